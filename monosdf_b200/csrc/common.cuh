@@ -1,0 +1,49 @@
+// Shared helpers for the monosdf_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/monosdf_b200.h"
+
+#define MSDF_OK 0
+#define MSDF_ERR_ARG 1
+#define MSDF_ERR_CUDA 2
+#define MSDF_ERR_UNSUPPORTED 3
+
+// Thread-local last error text, read through msdf_last_error() (api.cu).
+void msdf_set_error(const char* fmt, ...);
+
+#define MSDF_CHECK_ARG(cond, ...)                         \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            msdf_set_error(__VA_ARGS__);                  \
+            return MSDF_ERR_ARG;                          \
+        }                                                 \
+    } while (0)
+
+#define MSDF_CHECK_LAUNCH(name)                                                          \
+    do {                                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                             \
+        if (e_ != cudaSuccess) {                                                         \
+            msdf_set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e_));  \
+            return MSDF_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+
+#define MSDF_CUDA_CALL(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t e_ = (expr);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            msdf_set_error("%s failed: %s", #expr, cudaGetErrorString(e_));               \
+            return MSDF_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+static inline int64_t msdf_div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t msdf_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// kernel launch counter (bench.py reports gpu_launches from it)
+extern unsigned long long g_msdf_launches;
+#define MSDF_COUNT_LAUNCH() (++g_msdf_launches)

@@ -1,0 +1,231 @@
+// Laplace density + alpha compositing, forward and backward, one warp per ray.
+//
+// Replaces (reference code/): model/density.py:21-30 (LaplaceDensity), model/network.py:626-640
+// (volume_rendering) and the weighted sums / normal-map rotation of MonoSDFNetwork.forward :552-562,603-616.
+//   delta_i = z_{i+1} - z_i (last 1e10),  E_i = delta_i sigma_i,  T_i = exp(-sum_{j<i} E_j),  w_i = (1 - e^{-E_i}) T_i
+//   rgb = sum w c (+ (1 - sum w) bg),  depth = scale sum w z / (sum w + 1e-8),  normal = R^T sum w g/(|g| + 1e-6)
+// HBM-bound: per ray it reads S*(z, sdf, rgb3, grad3) = 32 S bytes and writes 4 S + 28 bytes (forward).
+#include "common.cuh"
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kWarps = 8;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFull, v, off);
+    return v;
+}
+__device__ __forceinline__ float warp_incl_scan(float v, int lane) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float t = __shfl_up_sync(kFull, v, off);
+        if (lane >= off) v += t;
+    }
+    return v;
+}
+
+struct Dens { float sigma, e; };   // sigma and exp(-|s|/beta)
+__device__ __forceinline__ Dens laplace(float s, float beta) {   // density.py:21-26
+    const float sg = (float)((s > 0.f) - (s < 0.f));
+    const float em1 = expm1f(-fabsf(s) / beta);
+    Dens d;
+    d.sigma = (1.0f / beta) * (0.5f + 0.5f * sg * em1);
+    d.e = em1 + 1.0f;
+    return d;
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_render_forward(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
+                 const float* __restrict__ grad, int64_t n_rays, int S, const float* __restrict__ beta_p,
+                 const float* __restrict__ depth_scale, int64_t ds_stride, const float* __restrict__ pose, int pose_per_ray,
+                 int white_bkgd, const float* __restrict__ bg, float* __restrict__ weights, float* __restrict__ rgb_values,
+                 float* __restrict__ depth_values, float* __restrict__ normal_map) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (r >= n_rays) return;
+    const float beta = *beta_p;
+    const float* zr = z + r * S; const float* sr = sdf + r * S;
+    float carry = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // rgb3, wz, w, n3
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < S;
+        float zi = 0.f, E = 0.f;
+        if (ok) {
+            zi = zr[i];
+            const float delta = (i < S - 1) ? zr[i + 1] - zi : 1e10f;
+            E = delta * laplace(sr[i], beta).sigma;
+        }
+        const float incl = warp_incl_scan(ok ? E : 0.f, lane);
+        const float excl = carry + incl - (ok ? E : 0.f);
+        carry += __shfl_sync(kFull, incl, 31);
+        if (ok) {
+            const float w = (1.0f - expf(-E)) * expf(-excl);
+            weights[r * S + i] = w;
+            const int64_t p = r * S + i;
+            acc[0] += w * rgb[3 * p]; acc[1] += w * rgb[3 * p + 1]; acc[2] += w * rgb[3 * p + 2];
+            acc[3] += w * zi; acc[4] += w;
+            const float gx = grad[3 * p], gy = grad[3 * p + 1], gz = grad[3 * p + 2];
+            const float q = w / (sqrtf(gx * gx + gy * gy + gz * gz) + 1e-6f);
+            acc[5] += q * gx; acc[6] += q * gy; acc[7] += q * gz;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = warp_sum(acc[k]);
+    if (lane == 0) {
+        float c[3] = {acc[0], acc[1], acc[2]};
+        if (white_bkgd) { const float t = 1.0f - acc[4]; c[0] += t * bg[0]; c[1] += t * bg[1]; c[2] += t * bg[2]; }
+        rgb_values[3 * r] = c[0]; rgb_values[3 * r + 1] = c[1]; rgb_values[3 * r + 2] = c[2];
+        depth_values[r] = depth_scale[r * ds_stride] * (acc[3] / (acc[4] + 1e-8f));
+        const float* P = pose + (pose_per_ray ? r * 16 : 0);
+        // normal_map = R^T n,  R = pose[:3,:3]   (network.py:608-616)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) normal_map[3 * r + a] = P[0 * 4 + a] * acc[5] + P[1 * 4 + a] * acc[6] + P[2 * 4 + a] * acc[7];
+    }
+}
+
+__global__ void __launch_bounds__(kWarps * 32)
+k_render_backward(const float* __restrict__ z, const float* __restrict__ sdf, const float* __restrict__ rgb,
+                  const float* __restrict__ grad, int64_t n_rays, int S, const float* __restrict__ beta_p,
+                  const float* __restrict__ depth_scale, int64_t ds_stride, const float* __restrict__ pose, int pose_per_ray,
+                  int white_bkgd, const float* __restrict__ bg, const float* __restrict__ d_weights,
+                  const float* __restrict__ d_rgbv, const float* __restrict__ d_depth, const float* __restrict__ d_nmap,
+                  float* __restrict__ d_sdf, float* __restrict__ d_rgb, float* __restrict__ d_grad, float* __restrict__ d_beta) {
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = (int64_t)blockIdx.x * kWarps + warp;
+    if (r >= n_rays) return;
+    float* sw = smem + (size_t)warp * 3 * S;   // w_i
+    float* sTe = sw + S;                      // T_i e^{-E_i}
+    float* sbw = sTe + S;                     // bar_w_i
+    const float beta = *beta_p;
+    const float* zr = z + r * S; const float* sr = sdf + r * S;
+    // pass 1: weights, sum w, sum w z
+    float carry = 0.f, W = 0.f, Z = 0.f;
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < S;
+        float zi = 0.f, E = 0.f;
+        if (ok) {
+            zi = zr[i];
+            const float delta = (i < S - 1) ? zr[i + 1] - zi : 1e10f;
+            E = delta * laplace(sr[i], beta).sigma;
+        }
+        const float incl = warp_incl_scan(ok ? E : 0.f, lane);
+        const float excl = carry + incl - (ok ? E : 0.f);
+        carry += __shfl_sync(kFull, incl, 31);
+        if (ok) {
+            const float T = expf(-excl), eE = expf(-E);
+            const float w = (1.0f - eE) * T;
+            sw[i] = w; sTe[i] = T * eE;
+            W += w; Z += w * zi;
+        }
+    }
+    W = warp_sum(W); Z = warp_sum(Z);
+    // adjoints of the ray outputs
+    float dc[3] = {0.f, 0.f, 0.f}, dv[3] = {0.f, 0.f, 0.f}, dd = 0.f;
+    if (d_rgbv) { dc[0] = d_rgbv[3 * r]; dc[1] = d_rgbv[3 * r + 1]; dc[2] = d_rgbv[3 * r + 2]; }
+    if (d_depth) dd = d_depth[r] * depth_scale[r * ds_stride];
+    if (d_nmap) {   // n_raw adjoint = R d_nmap
+        const float* P = pose + (pose_per_ray ? r * 16 : 0);
+        const float a0 = d_nmap[3 * r], a1 = d_nmap[3 * r + 1], a2 = d_nmap[3 * r + 2];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) dv[b] = P[b * 4 + 0] * a0 + P[b * 4 + 1] * a1 + P[b * 4 + 2] * a2;
+    }
+    const float Wq = W + 1e-8f;
+    float bgdot = 0.f;
+    if (white_bkgd) bgdot = dc[0] * bg[0] + dc[1] * bg[1] + dc[2] * bg[2];
+    // pass 2: bar_w, d_rgb, d_grad
+    float tot = 0.f;
+    for (int i = lane; i < S; i += 32) {
+        const int64_t p = r * S + i;
+        const float w = sw[i];
+        const float c0 = rgb[3 * p], c1 = rgb[3 * p + 1], c2 = rgb[3 * p + 2];
+        const float gx = grad[3 * p], gy = grad[3 * p + 1], gz = grad[3 * p + 2];
+        const float nrm = sqrtf(gx * gx + gy * gy + gz * gz), q = nrm + 1e-6f;
+        const float gv = gx * dv[0] + gy * dv[1] + gz * dv[2];
+        float bw = dc[0] * c0 + dc[1] * c1 + dc[2] * c2 - bgdot + dd * (zr[i] * Wq - Z) / (Wq * Wq) + gv / q;
+        if (d_weights) bw += d_weights[p];
+        sbw[i] = bw;
+        tot += bw * w;
+        if (d_rgb) { d_rgb[3 * p] = w * dc[0]; d_rgb[3 * p + 1] = w * dc[1]; d_rgb[3 * p + 2] = w * dc[2]; }
+        if (d_grad) {
+            const float k = nrm > 0.f ? gv / (nrm * q * q) : 0.f;
+            d_grad[3 * p] = w * (dv[0] / q - gx * k);
+            d_grad[3 * p + 1] = w * (dv[1] / q - gy * k);
+            d_grad[3 * p + 2] = w * (dv[2] / q - gz * k);
+        }
+    }
+    __syncwarp();
+    tot = warp_sum(tot);
+    // pass 3: bar_E_i = bar_w_i T_i e^{-E_i} - sum_{k>i} bar_w_k w_k  ->  d_sdf, d_beta
+    float carry2 = 0.f, dbeta = 0.f;
+    for (int base = 0; base < S; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < S;
+        const float t = ok ? sbw[i] * sw[i] : 0.f;
+        const float incl = carry2 + warp_incl_scan(t, lane);
+        carry2 = __shfl_sync(kFull, incl, 31);
+        if (ok) {
+            const float suffix = tot - incl;
+            const float bE = sbw[i] * sTe[i] - suffix;
+            const float delta = (i < S - 1) ? zr[i + 1] - zr[i] : 1e10f;
+            const float bs = bE * delta;                       // adjoint of sigma_i
+            const float s = sr[i];
+            const Dens d = laplace(s, beta);
+            const float ds = (s == 0.f) ? 0.f : -d.e / (2.0f * beta * beta);
+            const float db = -d.sigma / beta + s * d.e / (2.0f * beta * beta * beta);
+            // 0 * inf guards: when the adjoint is exactly zero the reference's autograd also yields 0 here only if
+            // the local derivative is finite, which it always is.
+            d_sdf[r * S + i] = bs * ds;
+            dbeta += bs * db;
+        }
+    }
+    if (d_beta) {
+        dbeta = warp_sum(dbeta);
+        if (lane == 0) atomicAdd(d_beta, dbeta);
+    }
+}
+
+}  // namespace
+
+extern "C" int msdf_render_forward(const float* z_vals, const float* sdf, const float* rgb, const float* grad, int64_t n_rays,
+                                   int n_samples, const float* beta, const float* depth_scale, int64_t depth_scale_stride,
+                                   const float* pose, int pose_per_ray, int white_bkgd, const float* bg_color, float* weights,
+                                   float* rgb_values, float* depth_values, float* normal_map, void* stream) {
+    MSDF_CHECK_ARG(z_vals && sdf && rgb && grad && beta && depth_scale && pose && weights && rgb_values && depth_values && normal_map,
+                   "msdf_render_forward: null pointer");
+    MSDF_CHECK_ARG(n_samples >= 1, "msdf_render_forward: n_samples=%d", n_samples);
+    MSDF_CHECK_ARG(!white_bkgd || bg_color, "msdf_render_forward: bg_color required with white_bkgd");
+    if (n_rays == 0) return MSDF_OK;
+    k_render_forward<<<(unsigned)msdf_div_up(n_rays, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(
+        z_vals, sdf, rgb, grad, n_rays, n_samples, beta, depth_scale, depth_scale_stride, pose, pose_per_ray, white_bkgd, bg_color,
+        weights, rgb_values, depth_values, normal_map);
+    MSDF_COUNT_LAUNCH();
+    MSDF_CHECK_LAUNCH("msdf_render_forward");
+    return MSDF_OK;
+}
+
+extern "C" int msdf_render_backward(const float* z_vals, const float* sdf, const float* rgb, const float* grad, int64_t n_rays,
+                                    int n_samples, const float* beta, const float* depth_scale, int64_t depth_scale_stride,
+                                    const float* pose, int pose_per_ray, int white_bkgd, const float* bg_color,
+                                    const float* d_weights, const float* d_rgb_values, const float* d_depth_values,
+                                    const float* d_normal_map, float* d_sdf, float* d_rgb, float* d_grad, float* d_beta,
+                                    void* stream) {
+    MSDF_CHECK_ARG(z_vals && sdf && rgb && grad && beta && depth_scale && pose && d_sdf, "msdf_render_backward: null pointer");
+    MSDF_CHECK_ARG(n_samples >= 1, "msdf_render_backward: n_samples=%d", n_samples);
+    MSDF_CHECK_ARG(!white_bkgd || bg_color, "msdf_render_backward: bg_color required with white_bkgd");
+    if (n_rays == 0) return MSDF_OK;
+    const size_t smem = (size_t)kWarps * 3 * n_samples * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_render_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { msdf_set_error("msdf_render_backward: %zu B shared memory: %s", smem, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
+    }
+    k_render_backward<<<(unsigned)msdf_div_up(n_rays, kWarps), kWarps * 32, smem, (cudaStream_t)stream>>>(
+        z_vals, sdf, rgb, grad, n_rays, n_samples, beta, depth_scale, depth_scale_stride, pose, pose_per_ray, white_bkgd, bg_color,
+        d_weights, d_rgb_values, d_depth_values, d_normal_map, d_sdf, d_rgb, d_grad, d_beta);
+    MSDF_COUNT_LAUNCH();
+    MSDF_CHECK_LAUNCH("msdf_render_backward");
+    return MSDF_OK;
+}
