@@ -33,6 +33,12 @@ int msdf_abi_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 unsigned long long msdf_launch_count(void);
 
+/* Per-launch device timing of the dominant kernels (CUDA events on the launching stream), for bench.py's roofline
+ * line.  class: 0 fp32 GEMM, 1 tensor-core GEMM, 2 hash grid, 3 sampler, 4 compositing.  work = FLOPs (GEMMs) or
+ * algorithmic bytes (the others) summed over the recorded launches. */
+int msdf_profile_enable(int on);
+int msdf_profile_read(int cls, double* total_ms, double* total_work, long long* count, int reset);
+
 /* ------------------------------------------------------------------ ray sampler ---------------------------
  * ErrorBoundSampler.get_z_vals, model/ray_sampler.py:110-262, split at the SDF evaluations.
  * Row buffers z/sdf are [n_rays, cap] with cap >= N_samples_eval * max_total_iters.                      */
@@ -162,6 +168,11 @@ int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* 
 /* points[r*n + j] = o[r] + z[r,j] * d[r]   (network.py:532-533, ray_sampler.py:129) */
 int msdf_ray_points(const float* ray_o, const float* ray_d, const float* z, int64_t n_rays, int n, float* points,
                     void* stream);
+
+/* rend_util.get_camera_params + lift (utils/rend_util.py:63-91,105-118), 4x4 poses: uv [B,N,2], pose [B,4,4],
+ * intrinsics [B,4,4] -> ray_dirs [B,N,3] (unit), cam_loc [B,3]. */
+int msdf_camera_rays(const float* uv, const float* pose, const float* intrinsics, int64_t batch, int64_t n_pixels,
+                     float* ray_dirs, float* cam_loc, void* stream);
 
 /* ------------------------------------------------------------------ compositing ---------------------------
  * LaplaceDensity (density.py:21-30) + volume_rendering (network.py:626-640) + the weighted sums and the

@@ -47,3 +47,9 @@ static inline size_t msdf_align(size_t x, size_t a = 256) { return (x + a - 1) /
 // kernel launch counter (bench.py reports gpu_launches from it)
 extern unsigned long long g_msdf_launches;
 #define MSDF_COUNT_LAUNCH() (++g_msdf_launches)
+
+// Optional per-launch device timing (CUDA events on the launching stream) of the dominant kernels, read by
+// bench.py for the roofline line.  Disabled by default: msdf_prof_begin returns -1 and records nothing.
+enum { MSDF_PROF_GEMM_F32 = 0, MSDF_PROF_GEMM_TC = 1, MSDF_PROF_HASH = 2, MSDF_PROF_SAMPLER = 3, MSDF_PROF_RENDER = 4, MSDF_PROF_CLASSES = 5 };
+int msdf_prof_begin(int cls, double work, cudaStream_t st);
+void msdf_prof_end(int slot, cudaStream_t st);

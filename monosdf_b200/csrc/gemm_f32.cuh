@@ -173,7 +173,9 @@ int launch(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, 
     kps = (kps + BK - 1) / BK * BK;
     splits = (int)((K + kps - 1) / kps);
     dim3 grid((unsigned)msdf_div_up(M, BM), (unsigned)msdf_div_up(N, BN), (unsigned)splits);
+    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_F32, 2.0 * (double)M * (double)N * (double)K, st);
     k_gemm<LAYOUT, Epi><<<grid, NT_THREADS, 0, st>>>(make_operand(A, lda), make_operand(B, ldb), M, N, K, kps, epi);
+    msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
     return MSDF_OK;

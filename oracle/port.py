@@ -563,7 +563,8 @@ def camera_rays(uv: Tensor, pose: Tensor, intrinsics: Tensor):
 # MonoSDFNetwork.forward (network.py:502-624)
 # --------------------------------------------------------------------------------------
 def model_forward(params: Dict[str, Tensor], cfg: ModelCfg, inp: Dict[str, Tensor], indices: Tensor,
-                  if_pixel_input: bool = False, training: bool = False, trace: Optional[dict] = None):
+                  if_pixel_input: bool = False, training: bool = False, trace: Optional[dict] = None,
+                  eik_points: Optional[Tensor] = None):
     if not if_pixel_input:
         ray_dirs, cam_loc = camera_rays(inp["uv"], inp["pose"], inp["intrinsics"])
         ray_dirs_tmp, _ = camera_rays(inp["uv"], torch.eye(4)[None], inp["intrinsics"])
@@ -604,6 +605,8 @@ def model_forward(params: Dict[str, Tensor], cfg: ModelCfg, inp: Dict[str, Tenso
         eik = torch.cat([eik, eik_near], 0)
         nei = eik + (torch.rand_like(eik) - 0.5) * 0.01
         eik = torch.cat([eik, nei], 0)
+        if eik_points is not None:   # tests inject the device-generated points of the CUDA run
+            eik = eik_points
         if trace is not None:
             trace["eik_points"] = eik.clone()
         gt = sdf_gradient(params, cfg, eik)
