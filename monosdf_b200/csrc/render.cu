@@ -57,8 +57,10 @@ k_render_forward(const float* __restrict__ z, const float* __restrict__ sdf, con
             const float delta = (i < S - 1) ? zr[i + 1] - zi : 1e10f;
             E = delta * laplace(sr[i], beta).sigma;
         }
+        // exclusive prefix by shifting the inclusive scan one lane (never subtract: E of the last sample is ~1e10)
         const float incl = warp_incl_scan(ok ? E : 0.f, lane);
-        const float excl = carry + incl - (ok ? E : 0.f);
+        const float prev = __shfl_up_sync(kFull, incl, 1);
+        const float excl = carry + (lane > 0 ? prev : 0.f);
         carry += __shfl_sync(kFull, incl, 31);
         if (ok) {
             const float w = (1.0f - expf(-E)) * expf(-excl);
@@ -112,8 +114,10 @@ k_render_backward(const float* __restrict__ z, const float* __restrict__ sdf, co
             const float delta = (i < S - 1) ? zr[i + 1] - zi : 1e10f;
             E = delta * laplace(sr[i], beta).sigma;
         }
+        // exclusive prefix by shifting the inclusive scan one lane (never subtract: E of the last sample is ~1e10)
         const float incl = warp_incl_scan(ok ? E : 0.f, lane);
-        const float excl = carry + incl - (ok ? E : 0.f);
+        const float prev = __shfl_up_sync(kFull, incl, 1);
+        const float excl = carry + (lane > 0 ? prev : 0.f);
         carry += __shfl_sync(kFull, incl, 31);
         if (ok) {
             const float T = expf(-excl), eE = expf(-E);
@@ -168,7 +172,8 @@ k_render_backward(const float* __restrict__ z, const float* __restrict__ sdf, co
         const float incl = carry2 + warp_incl_scan(t, lane);
         carry2 = __shfl_sync(kFull, incl, 31);
         if (ok) {
-            const float suffix = tot - incl;
+            // the last sample has no successors: keep its suffix EXACTLY zero (it is multiplied by delta = 1e10)
+            const float suffix = (i == S - 1) ? 0.f : tot - incl;
             const float bE = sbw[i] * sTe[i] - suffix;
             const float delta = (i < S - 1) ? zr[i + 1] - zr[i] : 1e10f;
             const float bs = bE * delta;                       // adjoint of sigma_i
