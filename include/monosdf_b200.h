@@ -204,9 +204,10 @@ int msdf_fused_adam(float* param, const float* grad, float* exp_avg, float* exp_
                     void* stream);
 
 /* ------------------------------------------------------------------ tensor-core path (bf16) ---------------
- * tcgen05/TMEM layer kernels; see monosdf_b200/csrc/tc_mlp.cu.  Declared in the same header so that the
- * symbol list is complete. */
-int msdf_tc_selftest(int variant, float* max_abs_err, void* stream);
+ * Self-test of the tcgen05 / TMEM / TMA GEMM engine (csrc/tc_gemm.cuh) against a naive kernel on the same bf16
+ * inputs.  variant selects a shape (forward-type GEMMs and weight-gradient GEMMs, ragged sizes included);
+ * result_host[0] = max |C - ref|, result_host[1] = max |ref| (HOST pointer, the call synchronises). */
+int msdf_tc_selftest(int variant, float* result_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -90,8 +90,3 @@ extern "C" int msdf_fused_adam(float* param, const float* grad, float* exp_avg, 
     return MSDF_OK;
 }
 
-extern "C" int msdf_tc_selftest(int variant, float* max_abs_err, void* stream) {
-    (void)variant; (void)max_abs_err; (void)stream;
-    msdf_set_error("msdf_tc_selftest: tensor-core path not built yet");
-    return MSDF_ERR_UNSUPPORTED;
-}

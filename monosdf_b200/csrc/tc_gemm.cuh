@@ -1,0 +1,450 @@
+// tcgen05 / TMEM / TMA GEMM engine for the MLP sweeps ("bf16 mode" of the field kernels), sm_100a only.
+//
+// Two persistent, warp-specialised kernels (1 CTA per SM, 320 threads: TMA producer warp, MMA issuer warp,
+// 8 epilogue warps):
+//
+//   k_tc_gemm   C[m, n] = epi( sum_k A[m,k] * W[n,k] )        A [M, K] bf16 K-major (activations),
+//               W [N<=256, K<=320] bf16 K-major: the layer's weights, loaded ONCE per CTA and kept resident in
+//               shared memory while the CTA walks over its 128-row tiles of A (4-stage TMA ring).  Accumulators
+//               live in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
+//               tile i+1.  Used by the forward / tangent sweeps (W = W_l) and the reverse / backward sweeps
+//               (W = W_l^T, transposed once per step by the weight-prep kernel).
+//
+//   k_tc_wgrad  dW[i, j] += sum_m X[m,i] * Y[m,j]             X [M, <=128 per tile], Y [M, <=256] bf16, both
+//               MN-major operands (the contraction runs over the rows = points), split over m across CTAs,
+//               fp32 atomics into dW.
+//
+// Shared-memory operand layout is the canonical UMMA SWIZZLE_128B layout written by TMA boxes of 64 bf16 (128 B)
+// inner extent; smem/instruction descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp.
+// Every mbarrier wait carries a clock watchdog that traps instead of hanging the GPU.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace msdf_tc {
+
+constexpr int BM = 128;            // rows per tile == TMEM lanes
+constexpr int BK = 64;             // bf16 per 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kStageBytesA = BM * BK * 2;   // 16 KB
+constexpr uint32_t kTmemCols = 512;
+
+// ----------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a protocol bug, fail loudly instead of hanging
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = lane = row)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): SWIZZLE_128B, Blackwell version bit
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;     // version_ = 1
+    d |= (uint64_t)2 << 61;     // layout_type_ = SWIZZLE_128B
+    return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M x N, operand majors
+__host__ __device__ inline uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// shared-memory carve-up
+// ----------------------------------------------------------------------------------------------------------
+struct Barriers {
+    uint64_t full[kMaxStages], empty[kMaxStages], bfull, tfull[2], tempty[2];
+    uint32_t tmem_base, pad;
+};
+
+// Epilogue concept: __device__ void operator()(int64_t m, int n, const float v[8]) const  -- row m, columns n..n+7
+// (n % 8 == 0; columns at or beyond the functor's own N must be masked by the functor).
+
+// ==========================================================================================================
+// C = epi(A W^T), weights resident
+// ==========================================================================================================
+template <class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, int64_t M, int BN, int KB,
+          int stages, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t sW = base;                                   // KB blocks of [BN rows x 128 B]
+    const uint32_t w_block = (uint32_t)BN * 128u;
+    const uint32_t sA = sW + (uint32_t)KB * w_block;            // stages x 16 KB
+    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)KB * w_block + (size_t)stages * kStageBytesA);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t num_tiles = (M + BM - 1) / BM;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA);
+        tma_prefetch_desc(&mapW);
+        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+        mbar_init(smem_u32(&bars->bfull), 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars->tfull[a]), 1); mbar_init(smem_u32(&bars->tempty[a]), kEpiWarps * 32); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- TMA producer: the layer's weights once, then the ring of A tiles
+            mbar_expect_tx(smem_u32(&bars->bfull), (uint32_t)KB * w_block);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * w_block, &mapW, smem_u32(&bars->bfull), kb * BK, 0);
+            int s = 0; uint32_t ph = 0;
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                    mbar_expect_tx(smem_u32(&bars->full[s]), kStageBytesA);
+                    tma_load_2d(sA + s * kStageBytesA, &mapA, smem_u32(&bars->full[s]), kb * BK, (int)(tile * BM));
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer
+            const uint32_t idesc = instr_desc(BM, BN, 0, 0);
+            mbar_wait(smem_u32(&bars->bfull), 0);
+            int s = 0; uint32_t ph = 0; uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+                const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait(smem_u32(&bars->tempty[a]), aph ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + a * 256u;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(smem_u32(&bars->full[s]), ph);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = smem_desc(sA + s * kStageBytesA + k * (UMMA_K * 2), 16, 1024);
+                        const uint64_t db = smem_desc(sW + kb * w_block + k * (UMMA_K * 2), 16, 1024);
+                        umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&bars->empty[s]));
+                    if (++s == stages) { s = 0; ph ^= 1u; }
+                }
+                umma_commit(smem_u32(&bars->tfull[a]));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- epilogue: TMEM lane quadrant = warp % 4; the two warps of a quadrant interleave 32-column chunks
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int chunks = (BN + 31) / 32;
+        uint32_t it = 0;
+        for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+            mbar_wait(smem_u32(&bars->tfull[a]), aph);
+            tc_fence_after();
+            const int64_t row = tile * BM + q * 32 + lane;
+            for (int c = half; c < chunks; c += 2) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u + (uint32_t)c * 32u, v);
+                if (row < M) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) epi(row, c * 32 + g * 8, v + g * 8);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(smem_u32(&bars->tempty[a]));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ==========================================================================================================
+// dW += X^T Y  (both operands MN-major), split over the rows
+// ==========================================================================================================
+// grid (i_tiles, j_tiles, splits).  X tile: BI = 128 columns of X = 2 boxes of [64 rows(k) x 64 cols]; Y tile: BJ
+// columns (multiple of 64, <= 256) = BJ/64 boxes.  One k-block = 64 rows.
+template <class Epi>
+__global__ void __launch_bounds__(kThreads, 1)
+k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int BJ,
+           int64_t rows_per_split, int stages, Epi epi) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    constexpr uint32_t kBox = 64 * 128;                          // 64 k-rows x 128 B
+    const uint32_t nbx = 2, nby = (uint32_t)BJ / 64u;
+    const uint32_t stage_bytes = (nbx + nby) * kBox;
+    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)stages * stage_bytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i0 = blockIdx.x * 128, j0 = blockIdx.y * BJ;
+    const int64_t r0 = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t r1 = (r0 + rows_per_split < Mrows) ? r0 + rows_per_split : Mrows;
+    const int nkb = r1 > r0 ? (int)((r1 - r0 + 63) / 64) : 0;   // the last block of a split may run past r1: the host
+                                                                 // makes rows_per_split a multiple of 64, so only the
+                                                                 // global tail is ragged and TMA zero-fills it
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapY);
+        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+        mbar_init(smem_u32(&bars->tfull[0]), 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
+                mbar_expect_tx(smem_u32(&bars->full[s]), stage_bytes);
+                const uint32_t st = base + s * stage_bytes;
+                const int row = (int)(r0 + (int64_t)kb * 64);
+                for (uint32_t b = 0; b < nbx; ++b) tma_load_2d(st + b * kBox, &mapX, smem_u32(&bars->full[s]), i0 + (int)b * 64, row);
+                for (uint32_t b = 0; b < nby; ++b) tma_load_2d(st + (nbx + b) * kBox, &mapY, smem_u32(&bars->full[s]), j0 + (int)b * 64, row);
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && nkb > 0) {
+            const uint32_t idesc = instr_desc(128, BJ, 1, 1);
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(smem_u32(&bars->full[s]), ph);
+                tc_fence_after();
+                const uint32_t st = base + s * stage_bytes;
+#pragma unroll
+                for (int k = 0; k < 64 / UMMA_K; ++k) {
+                    // MN-major SW128: 64-element groups along M/N are kBox apart (LBO), 8-row k groups 1024 B apart (SBO)
+                    const uint64_t da = smem_desc(st + k * (UMMA_K * 128), kBox, 1024);
+                    const uint64_t db = smem_desc(st + nbx * kBox + k * (UMMA_K * 128), kBox, 1024);
+                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&bars->empty[s]));
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+            umma_commit(smem_u32(&bars->tfull[0]));
+        }
+        __syncwarp();
+    } else if (nkb > 0) {
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int chunks = (BJ + 31) / 32;
+        mbar_wait(smem_u32(&bars->tfull[0]), 0);
+        tc_fence_after();
+        const int64_t row = i0 + q * 32 + lane;
+        for (int c = half; c < chunks; c += 2) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 32u, v);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) epi(row, j0 + c * 32 + g * 8, v + g * 8);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64 cols], 128-byte swizzle
+inline int make_map(CUtensorMap* map, const __nv_bfloat16* p, int64_t rows, int64_t cols, int64_t ld, int box_rows, const char* who) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { msdf_set_error("%s: cuTensorMapEncodeTiled is unavailable", who); return MSDF_ERR_CUDA; }
+    if ((((uintptr_t)p) & 15) != 0 || (ld % 8) != 0) { msdf_set_error("%s: TMA operand must be 16-byte aligned (ld %% 8 == 0)", who); return MSDF_ERR_ARG; }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { msdf_set_error("%s: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", who, (int)r,
+                                            (long long)rows, (long long)cols, (long long)ld, box_rows); return MSDF_ERR_CUDA; }
+    return MSDF_OK;
+}
+
+inline int sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+// C = epi(A W^T): A [M, Kp] (ld lda), W [BN, Kp] (ld ldw); Kp multiple of 64 (<= 320), BN multiple of 16 (<= 256)
+template <class Epi>
+int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __nv_bfloat16* W, int64_t ldw, int BN, const Epi& epi,
+                cudaStream_t st, const char* what) {
+    if (M <= 0) return MSDF_OK;
+    if (Kp % 64 != 0 || Kp <= 0 || Kp > 320 || BN % 16 != 0 || BN < 16 || BN > 256) {
+        msdf_set_error("%s: tensor-core GEMM needs K %% 64 == 0 (<= 320) and N %% 16 == 0 (<= 256); got K=%d N=%d", what, Kp, BN);
+        return MSDF_ERR_ARG;
+    }
+    CUtensorMap mA, mW;
+    int rc = make_map(&mA, A, M, Kp, lda, BM, what); if (rc) return rc;
+    rc = make_map(&mW, W, BN, Kp, ldw, BN, what); if (rc) return rc;
+    const int KB = Kp / 64;
+    const size_t wbytes = (size_t)KB * BN * 128;
+    int stages = (int)((227 * 1024 - 1024 - sizeof(Barriers) - wbytes) / kStageBytesA);
+    if (stages > 6) stages = 6;
+    if (stages < 2) { msdf_set_error("%s: weights do not leave room for the A ring", what); return MSDF_ERR_ARG; }
+    const size_t smem = 1024 + wbytes + (size_t)stages * kStageBytesA + sizeof(Barriers);
+    static bool attr_set = false;   // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { msdf_set_error("%s: cannot opt in to 227 KB shared memory: %s", what, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
+        attr_set = true;
+    }
+    const int64_t tiles = (M + BM - 1) / BM;
+    const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st);
+    k_tc_gemm<Epi><<<grid, kThreads, smem, st>>>(mA, mW, M, BN, KB, stages, epi);
+    msdf_prof_end(prof, st);
+    MSDF_COUNT_LAUNCH();
+    MSDF_CHECK_LAUNCH(what);
+    return MSDF_OK;
+}
+
+// dW[i,j] (+)= sum_m X[m,i] Y[m,j]: X [M, Ci] (ld ldx), Y [M, Cj] (ld ldy), Ci / Cj = padded column counts (multiples
+// of 64); the functor masks i / j beyond the real sizes and accumulates atomically.
+template <class Epi>
+int launch_wgrad(const __nv_bfloat16* X, int64_t ldx, int Ci, const __nv_bfloat16* Y, int64_t ldy, int Cj, int64_t M, const Epi& epi,
+                 cudaStream_t st, const char* what) {
+    if (M <= 0) return MSDF_OK;
+    if (Ci % 64 != 0 || Cj % 64 != 0 || Ci <= 0 || Cj <= 0) { msdf_set_error("%s: wgrad needs column counts %% 64 == 0", what); return MSDF_ERR_ARG; }
+    CUtensorMap mX, mY;
+    int rc = make_map(&mX, X, M, Ci, ldx, 64, what); if (rc) return rc;
+    rc = make_map(&mY, Y, M, Cj, ldy, 64, what); if (rc) return rc;
+    const int BJ = Cj < 256 ? Cj : 256;
+    const int it = (Ci + 127) / 128, jt = (Cj + BJ - 1) / BJ;
+    int splits = (sm_count() + it * jt - 1) / (it * jt);
+    int64_t rps = (M + splits - 1) / splits;
+    rps = (rps + 63) / 64 * 64;
+    if (rps < 256) rps = 256;
+    splits = (int)((M + rps - 1) / rps);
+    const uint32_t stage_bytes = (2 + BJ / 64) * 64 * 128;
+    int stages = (int)((227 * 1024 - 1024 - sizeof(Barriers)) / stage_bytes);
+    if (stages > 6) stages = 6;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + sizeof(Barriers);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { msdf_set_error("%s: cannot opt in to 227 KB shared memory: %s", what, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
+    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st);
+    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, epi);
+    msdf_prof_end(prof, st);
+    MSDF_COUNT_LAUNCH();
+    MSDF_CHECK_LAUNCH(what);
+    return MSDF_OK;
+}
+
+}  // namespace msdf_tc

@@ -1,0 +1,113 @@
+// Self-test of the tcgen05 GEMM engine (tc_gemm.cuh) against a naive fp32-accumulate kernel on the same bf16
+// inputs.  Test infrastructure reachable through the C ABI (msdf_tc_selftest) so that the -m gpu tests can pin the
+// UMMA descriptors / TMA layouts before the sweeps use them.
+#include "tc_gemm.cuh"
+
+namespace {
+using bf16 = __nv_bfloat16;
+
+__global__ void k_fill(bf16* p, int64_t n, uint32_t seed, float scale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t x = (uint32_t)i * 747796405u + seed * 2891336453u + 12345u;
+    x ^= x >> 17; x *= 0xed5ad4bbu; x ^= x >> 11; x *= 0xac4c1b51u; x ^= x >> 15;
+    p[i] = __float2bfloat16(((x & 0xffff) / 65536.0f - 0.5f) * scale);
+}
+// C[m,n] = sum_k A[m,k] W[n,k]
+__global__ void k_ref_gemm(const bf16* A, int64_t lda, const bf16* W, int64_t ldw, int64_t M, int N, int K, float* C, int64_t ldc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * N) return;
+    const int64_t m = i / N; const int n = (int)(i - m * N);
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s = fmaf(__bfloat162float(A[m * lda + k]), __bfloat162float(W[(int64_t)n * ldw + k]), s);
+    C[m * ldc + n] = s;
+}
+// C[i,j] = sum_m X[m,i] Y[m,j]
+__global__ void k_ref_wgrad(const bf16* X, int64_t ldx, const bf16* Y, int64_t ldy, int64_t M, int Ni, int Nj, float* C, int64_t ldc) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Ni * Nj) return;
+    const int i = idx / Nj, j = idx - i * Nj;
+    float s = 0.f;
+    for (int64_t m = 0; m < M; ++m) s = fmaf(__bfloat162float(X[m * ldx + i]), __bfloat162float(Y[m * ldy + j]), s);
+    C[(int64_t)i * ldc + j] = s;
+}
+__global__ void k_maxerr(const float* a, const float* b, int64_t n, float* out) {   // out[0] = max |a-b|, out[1] = max |b|
+    float e = 0.f, r = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = fabsf(a[i] - b[i]);
+        e = (d > e || d != d) ? d : e;
+        r = fmaxf(r, fabsf(b[i]));
+    }
+    atomicMax(reinterpret_cast<int*>(out), __float_as_int(e != e ? INFINITY : e));
+    atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(r));
+}
+
+struct EpiStore {
+    float* C; int64_t ldc; int N;
+    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[8]) const {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (n + j < N) C[m * ldc + n + j] = v[j];
+    }
+};
+struct EpiAtomicAdd {
+    float* C; int64_t ldc; int Ni, Nj;
+    __device__ __forceinline__ void operator()(int64_t i, int n, const float v[8]) const {
+        if (i >= Ni) return;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (n + j < Nj) atomicAdd(C + i * ldc + n + j, v[j]);
+    }
+};
+
+struct Case { int kind; int64_t M; int N, K; int Np, Kp; };   // kind 0: gemm (N x K weights), 1: wgrad (Ni = N, Nj = K)
+const Case kCases[] = {
+    {0, 1000, 256, 256, 256, 256},
+    {0, 128 * 150 + 77, 217, 39, 224, 64},
+    {0, 40000, 64, 289, 64, 320},
+    {0, 128 * 600, 256, 256, 256, 256},
+    {1, 5000, 256, 256, 256, 256},
+    {1, 70001, 257, 39, 320, 64},
+    {1, 300, 64, 256, 64, 256},
+    {1, 262144, 256, 256, 256, 256},
+};
+}  // namespace
+
+extern "C" int msdf_tc_selftest(int variant, float* result_host, void* stream) {
+    const int ncases = (int)(sizeof(kCases) / sizeof(kCases[0]));
+    MSDF_CHECK_ARG(variant >= 0 && variant < ncases && result_host, "msdf_tc_selftest: variant must be in [0,%d)", ncases);
+    const Case c = kCases[variant];
+    cudaStream_t st = (cudaStream_t)stream;
+    bf16 *A = nullptr, *B = nullptr; float *C = nullptr, *R = nullptr, *out = nullptr;
+    int rc = MSDF_OK;
+    if (c.kind == 0) {
+        const int64_t lda = c.Kp, ldw = c.Kp, ldc = c.Np;
+        MSDF_CUDA_CALL(cudaMalloc(&A, c.M * lda * 2)); MSDF_CUDA_CALL(cudaMalloc(&B, (int64_t)c.Np * ldw * 2));
+        MSDF_CUDA_CALL(cudaMalloc(&C, c.M * ldc * 4)); MSDF_CUDA_CALL(cudaMalloc(&R, c.M * ldc * 4)); MSDF_CUDA_CALL(cudaMalloc(&out, 8));
+        k_fill<<<(unsigned)msdf_div_up(c.M * lda, 256), 256, 0, st>>>(A, c.M * lda, 1, 2.0f);
+        k_fill<<<(unsigned)msdf_div_up((int64_t)c.Np * ldw, 256), 256, 0, st>>>(B, (int64_t)c.Np * ldw, 2, 1.0f);
+        MSDF_CUDA_CALL(cudaMemsetAsync(C, 0, c.M * ldc * 4, st)); MSDF_CUDA_CALL(cudaMemsetAsync(R, 0, c.M * ldc * 4, st));
+        MSDF_CUDA_CALL(cudaMemsetAsync(out, 0, 8, st));
+        // the padded K columns of A hold random (finite) data: zero the padded K columns of the weights instead
+        k_ref_gemm<<<(unsigned)msdf_div_up(c.M * c.N, 256), 256, 0, st>>>(A, lda, B, ldw, c.M, c.N, c.Kp, R, ldc);
+        EpiStore e{C, ldc, c.N};
+        rc = msdf_tc::launch_gemm(A, lda, c.M, c.Kp, B, ldw, c.Np, e, st, "msdf_tc_selftest(gemm)");
+        if (!rc) k_maxerr<<<256, 256, 0, st>>>(C, R, c.M * ldc, out);
+    } else {
+        const int64_t ldx = c.Np, ldy = c.Kp, ldc = c.K;
+        MSDF_CUDA_CALL(cudaMalloc(&A, c.M * ldx * 2)); MSDF_CUDA_CALL(cudaMalloc(&B, c.M * ldy * 2));
+        MSDF_CUDA_CALL(cudaMalloc(&C, (int64_t)c.N * ldc * 4)); MSDF_CUDA_CALL(cudaMalloc(&R, (int64_t)c.N * ldc * 4)); MSDF_CUDA_CALL(cudaMalloc(&out, 8));
+        k_fill<<<(unsigned)msdf_div_up(c.M * ldx, 256), 256, 0, st>>>(A, c.M * ldx, 3, 1.0f);
+        k_fill<<<(unsigned)msdf_div_up(c.M * ldy, 256), 256, 0, st>>>(B, c.M * ldy, 4, 1.0f);
+        MSDF_CUDA_CALL(cudaMemsetAsync(C, 0, (int64_t)c.N * ldc * 4, st)); MSDF_CUDA_CALL(cudaMemsetAsync(out, 0, 8, st));
+        k_ref_wgrad<<<(unsigned)msdf_div_up((int64_t)c.N * c.K, 128), 128, 0, st>>>(A, ldx, B, ldy, c.M, c.N, c.K, R, ldc);
+        EpiAtomicAdd e{C, ldc, c.N, c.K};
+        rc = msdf_tc::launch_wgrad(A, ldx, c.Np, B, ldy, c.Kp, c.M, e, st, "msdf_tc_selftest(wgrad)");
+        if (!rc) k_maxerr<<<64, 256, 0, st>>>(C, R, (int64_t)c.N * ldc, out);
+    }
+    cudaError_t e2 = cudaStreamSynchronize(st);
+    if (!rc && e2 != cudaSuccess) { msdf_set_error("msdf_tc_selftest: kernel failed: %s", cudaGetErrorString(e2)); rc = MSDF_ERR_CUDA; }
+    if (!rc) cudaMemcpy(result_host, out, 8, cudaMemcpyDeviceToHost);
+    cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(R); cudaFree(out);
+    return rc;
+}
