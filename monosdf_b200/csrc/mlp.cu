@@ -12,7 +12,15 @@
 //   weight grads    dW_l += pbar_l^T u_l + a_l^T t_l,  db_l += colsum(pbar_l)
 // where sigma_l = sigmoid(100 p_l) is recovered from the stored post-activation as -expm1(-100 h).
 // Nothing is kept between forward and backward: the backward recomputes the chunk.
+//
+// The sweeps are written once, generic over the activation element type T:
+//   T = float          fp32 mode: SIMT FFMA GEMMs (gemm_f32.cuh), the reference's arithmetic class (1e-4 parity)
+//   T = __nv_bfloat16  bf16 mode: tcgen05 tensor-core GEMMs with TMEM accumulators and TMA-fed operands
+//                      (tc_gemm.cuh), activations stored in bf16, fp32 accumulation (2e-2 parity)
+#include <type_traits>
+
 #include "gemm_f32.cuh"
+#include "tc_gemm.cuh"
 
 int msdf_hash_forward_rows(const float* x, const float* table, const int* offsets, float* out, int64_t out_ld,
                            int64_t B, int C, int L, float S, uint32_t H, float divide_factor, float* dy_dx, cudaStream_t st);
@@ -22,45 +30,116 @@ int msdf_hash_scatter_rows(const float* x, const int* offsets, int64_t B, int C,
 
 namespace {
 
-using namespace msdf_gemm;
+using bf16 = __nv_bfloat16;
+using msdf_gemm::kNN;
+using msdf_gemm::kNT;
+using msdf_gemm::kTN;
 
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr float kSqrt2 = 1.41421356237309504880f;
 
+template <class T> constexpr bool kIsBf16 = std::is_same<T, bf16>::value;
+
+// ----------------------------------------------------------------------------------------------------------
+// element access
+// ----------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16(v); }
+
+// W consecutive elements of a row; vectorised when the whole group is valid and 16-byte aligned
+template <int W>
+__device__ __forceinline__ void load_row(const float* p, float* o, int nv) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] = j < nv ? p[j] : 0.f;
+}
+template <int W>
+__device__ __forceinline__ void load_row(const bf16* p, float* o, int nv) {
+    if (W == 8 && nv == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[2 * j] = __uint_as_float(w[j] << 16);
+            o[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] = j < nv ? __bfloat162float(p[j]) : 0.f;
+}
+template <int W>
+__device__ __forceinline__ void store_row(float* p, const float* v, int nv) {
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+        if (j < nv) p[j] = v[j];
+}
+template <int W>
+__device__ __forceinline__ void store_row(bf16* p, const float* v, int nv) {
+    if (W == 8 && nv == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            w[j] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+        if (j < nv) p[j] = __float2bfloat16(v[j]);
+}
+
+// activation math.  FAST = bf16 mode: MUFU ex2/lg2 approximations (error far below bf16 resolution);
+// precise (libdevice) otherwise.
+template <bool FAST>
 __device__ __forceinline__ float softplus100(float p) {   // nn.Softplus(beta=100), threshold 20 (network.py:77)
     const float bp = 100.f * p;
+    if (FAST) return bp > 20.f ? p : fmaxf(p, 0.f) + __logf(1.0f + __expf(-fabsf(bp))) * 0.01f;
     return bp > 20.f ? p : log1pf(expf(bp)) / 100.f;
 }
 // sigmoid(100 p) from h = softplus100(p):  1 - exp(-100 h)
-__device__ __forceinline__ float sig_from_h(float h) { return -expm1f(-100.f * h); }
-// 100 * (1 - sigmoid(100 p)) from h;  exactly 0 past the softplus threshold like torch's double backward
-__device__ __forceinline__ float dsig_over_sig_from_h(float h) {
+template <bool FAST>
+__device__ __forceinline__ float sig_from_h(float h) { return FAST ? 1.0f - __expf(-100.f * h) : -expm1f(-100.f * h); }
+// (sigmoid, 100 (1 - sigmoid)) from h; the second is exactly 0 past the softplus threshold like torch's double backward
+template <bool FAST>
+__device__ __forceinline__ void sig_dsig_from_h(float h, float& s, float& d) {
     const float t = 100.f * h;
-    return t > 20.f ? 0.f : 100.f * expf(-t);
+    const float e = FAST ? __expf(-t) : expf(-t);
+    s = FAST ? 1.0f - e : -expm1f(-t);
+    d = t > 20.f ? 0.f : 100.f * e;
 }
 
 // ----------------------------------------------------------------------------------------------------------
 // network geometry
 // ----------------------------------------------------------------------------------------------------------
 struct Net {
-    int L, d0, d0p, skip, ldh;
+    int L, d0, skip;
     int in[MSDF_MAX_LAYERS], out[MSDF_MAX_LAYERS];
     int64_t ldw[MSDF_MAX_LAYERS];
     const float* W[MSDF_MAX_LAYERS];
     const float* b[MSDF_MAX_LAYERS];
+    int maxw;
+    // bf16 copies for the tensor-core path (prepared per call): Wk = W (K-major over the inputs), Wt = W^T
+    bf16* Wk[MSDF_MAX_LAYERS]; bf16* Wt[MSDF_MAX_LAYERS];
+    int perm_last;     // 1: rows of the last layer are ordered [features..., sdf] in Wk/Wt (bf16 SDF net)
 };
 
-inline int round4(int x) { return (x + 3) / 4 * 4; }
+inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
+template <class T> inline int padw(int n) { return kIsBf16<T> ? round_up(n, 64) : round_up(n, 4); }
 
 int make_net(const msdf_mlp_desc* d, Net& n, const char* who) {
     MSDF_CHECK_ARG(d != nullptr, "%s: null network descriptor", who);
     MSDF_CHECK_ARG(d->n_layers >= 2 && d->n_layers <= MSDF_MAX_LAYERS, "%s: n_layers=%d not in [2,%d]", who, d->n_layers,
                    MSDF_MAX_LAYERS);
-    n.L = d->n_layers; n.d0 = d->d0; n.d0p = round4(d->d0); n.skip = d->skip_layer;
+    n.L = d->n_layers; n.d0 = d->d0; n.skip = d->skip_layer; n.perm_last = 0;
     MSDF_CHECK_ARG(n.skip < n.L && n.skip != 0, "%s: skip_layer=%d invalid", who, n.skip);
     int w = 0;
     for (int l = 0; l < n.L; ++l) {
         n.in[l] = d->in_dim[l]; n.out[l] = d->out_dim[l]; n.ldw[l] = d->ldw[l]; n.W[l] = d->W[l]; n.b[l] = d->b[l];
+        n.Wk[l] = n.Wt[l] = nullptr;
         MSDF_CHECK_ARG(n.W[l] && n.b[l], "%s: layer %d has null weights", who, l);
         MSDF_CHECK_ARG(n.ldw[l] >= n.in[l] && n.in[l] > 0 && n.out[l] > 0, "%s: layer %d bad dims", who, l);
         const int expect = (l == 0) ? n.d0 : (l == n.skip ? n.out[l - 1] + n.d0 : n.out[l - 1]);
@@ -68,12 +147,21 @@ int make_net(const msdf_mlp_desc* d, Net& n, const char* who) {
         if (l > 0) w = w > n.in[l] ? w : n.in[l];
         if (l < n.L - 1) w = w > n.out[l] ? w : n.out[l];
     }
-    n.ldh = round4(w);
+    n.maxw = w;
+    return MSDF_OK;
+}
+
+// the tensor-core path keeps whole rows of every operand in 64-column TMA boxes
+int check_tc_net(const Net& n, const char* who) {
+    for (int l = 1; l < n.L; ++l)
+        MSDF_CHECK_ARG(n.in[l] % 64 == 0 && n.in[l] <= 256, "%s: bf16 mode needs hidden widths that are multiples of 64 (<= 256); layer %d has %d",
+                       who, l, n.in[l]);
+    MSDF_CHECK_ARG(n.in[0] <= 320 && n.out[n.L - 1] <= 320, "%s: bf16 mode supports at most 320 input / output columns", who);
     return MSDF_OK;
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// encoding kernels  (embedder.py:5-50; hash features are written by hashgrid.cu)
+// encoding kernels  (embedder.py:5-50; hash features come from hashgrid.cu)
 // ----------------------------------------------------------------------------------------------------------
 // value / derivative of PE column j (< 3 + 6*multires) at x: column order [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...]
 __device__ __forceinline__ float pe_value(const float x[3], int j) {
@@ -91,29 +179,39 @@ __device__ __forceinline__ float pe_deriv(const float x[3], int j) {
     return r < 3 ? f * cosf(x[r] * f) : -f * sinf(x[r - 3] * f);
 }
 
-// H0[m, j] = PE_j(x_m) for j < pe_w   (hash columns are filled by msdf_hash_forward_rows; padding untouched)
-__global__ void k_encode(const float* __restrict__ x, int64_t M, int pe_w, float* __restrict__ H0, int64_t ld0) {
+// H0[m, j] for j < cols: PE(x_m), then hash features (from hashf, or zeros), then zero padding
+template <class T>
+__global__ void k_encode(const float* __restrict__ x, int64_t M, int pe_w, int grid_w, const float* __restrict__ hashf,
+                         T* __restrict__ H0, int64_t ld0, int cols) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M * pe_w) return;
-    const int64_t m = i / pe_w; const int j = (int)(i - m * pe_w);
-    const float p[3] = {x[3 * m], x[3 * m + 1], x[3 * m + 2]};
-    H0[m * ld0 + j] = pe_value(p, j);
+    if (i >= M * cols) return;
+    const int64_t m = i / cols; const int j = (int)(i - m * cols);
+    float v = 0.f;
+    if (j < pe_w) {
+        const float p[3] = {x[3 * m], x[3 * m + 1], x[3 * m + 2]};
+        v = pe_value(p, j);
+    } else if (j < pe_w + grid_w && hashf != nullptr) {
+        v = hashf[m * grid_w + (j - pe_w)];
+    }
+    stf(H0 + m * ld0 + j, v);
 }
 
-__global__ void k_zero_cols(float* __restrict__ dst, int64_t ld, int64_t M, int c0, int w) {
+template <class T>
+__global__ void k_zero_cols(T* __restrict__ dst, int64_t ld, int64_t M, int c0, int w) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * w) return;
     const int64_t m = i / w; const int j = (int)(i - m * w);
-    dst[m * ld + c0 + j] = 0.f;
+    stf(dst + m * ld + c0 + j, 0.f);
 }
 
 // dst[m, c0 + j] = src[m, j] * scale   (the [.., h0]/sqrt2 half of the skip concat, network.py:88-89)
-__global__ void k_skip_copy(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t M,
-                            int w, int c0, float scale) {
+template <class T>
+__global__ void k_skip_copy(const T* __restrict__ src, int64_t lds, T* __restrict__ dst, int64_t ldd, int64_t M, int w, int c0,
+                            float scale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * w) return;
     const int64_t m = i / w; const int j = (int)(i - m * w);
-    dst[m * ldd + c0 + j] = src[m * lds + j] * scale;
+    stf(dst + m * ldd + c0 + j, ldf(src + m * lds + j) * scale);
 }
 
 // grad_x = J_enc(x)^T g0 (+ hash chain), then the bounding-sphere clamp of get_outputs (network.py:116-118):
@@ -157,16 +255,17 @@ __global__ void k_decode(const float* __restrict__ x, const float* __restrict__ 
     if (mask_out) mask_out[m] = mk;
 }
 
-// Backward prologue: dn[m] = mask * (d_grad[m] + dn_color[m]);  Dout[m,0] = mask * d_sdf[m];
-//   Dout[m,1+j] (+)= d_feat[m,j];   TG0[m, j] = (J_enc dn)[j]  -- the tangent of the encoded input.
+// Backward prologue: dn[m] = mask * (d_grad[m] + dn_color[m]);  Dout[m, sdf_col] = mask * d_sdf[m];
+//   Dout[m, feat_col0 + j] (+)= d_feat[m,j], remaining columns of Dout zero;  TG0[m, :] = J_enc dn (zero padded).
+template <class T>
 __global__ void k_backward_prologue(const float* __restrict__ x, int64_t M, int pe_w, int grid_w, int n_levels, int level_dim,
                                     const float* __restrict__ dy_dx, float hash_chain, const float* __restrict__ mask,
                                     const float* __restrict__ d_sdf, const float* __restrict__ d_grad,
                                     const float* __restrict__ dn_color, const float* __restrict__ d_feat, int64_t ld_dfeat,
-                                    int feat_w, int have_color_feat, float* __restrict__ Dout, int64_t ldo,
-                                    float* __restrict__ dn, float* __restrict__ TG0, int64_t ldt) {
+                                    int feat_w, int have_color_feat, int sdf_col, int feat_col0, T* __restrict__ Dout, int64_t ldo,
+                                    int out_cols, float* __restrict__ dn, T* __restrict__ TG0, int64_t ldt, int t_cols) {
     const int d0 = pe_w + grid_w;
-    const int cols = d0 > feat_w + 1 ? d0 : feat_w + 1;
+    const int cols = t_cols > out_cols ? t_cols : out_cols;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * cols) return;
     const int64_t m = i / cols; const int j = (int)(i - m * cols);
@@ -176,38 +275,39 @@ __global__ void k_backward_prologue(const float* __restrict__ x, int64_t M, int 
     for (int d = 0; d < 3; ++d)
         v[d] = mk * ((d_grad ? d_grad[3 * m + d] : 0.f) + (dn_color ? dn_color[3 * m + d] : 0.f));
     if (j < 3) dn[3 * m + j] = v[j];
-    if (j == 0) Dout[m * ldo] = d_sdf ? mk * d_sdf[m] : 0.f;
-    if (j >= 1 && j <= feat_w) {
-        float f = have_color_feat ? Dout[m * ldo + j] : 0.f;
-        if (d_feat) f += d_feat[m * ld_dfeat + (j - 1)];
-        Dout[m * ldo + j] = f;
+    if (j < out_cols) {
+        float f = 0.f;
+        if (j == sdf_col) f = d_sdf ? mk * d_sdf[m] : 0.f;
+        else if (j >= feat_col0 && j < feat_col0 + feat_w) {
+            if (have_color_feat) f = ldf(Dout + m * ldo + j);
+            if (d_feat) f += d_feat[m * ld_dfeat + (j - feat_col0)];
+        }
+        stf(Dout + m * ldo + j, f);
     }
-    if (j < d0) {
-        float t;
+    if (j < t_cols) {
+        float t = 0.f;
         if (j < pe_w) {
             const float p[3] = {x[3 * m], x[3 * m + 1], x[3 * m + 2]};
             t = pe_deriv(p, j) * v[pe_dim(j)];
-        } else {
+        } else if (j < d0 && dy_dx != nullptr) {
             const int q = j - pe_w, l = q / level_dim, c = q - l * level_dim;
-            t = 0.f;
-            if (dy_dx != nullptr) {
-                const float* dd = dy_dx + m * (int64_t)(n_levels * 3 * level_dim) + (l * 3) * level_dim + c;
-                t = (dd[0] * v[0] + dd[level_dim] * v[1] + dd[2 * level_dim] * v[2]) * hash_chain;
-            }
+            const float* dd = dy_dx + m * (int64_t)(n_levels * 3 * level_dim) + (l * 3) * level_dim + c;
+            t = (dd[0] * v[0] + dd[level_dim] * v[1] + dd[2 * level_dim] * v[2]) * hash_chain;
         }
-        TG0[m * ldt + j] = t;
+        stf(TG0 + m * ldt + j, t);
     }
 }
 
 // out[n] += sum_m w[m*ws] * X[m*ldx + n]   (w == nullptr -> 1).  Bias gradients and the sdf row of the last layer.
+template <class T>
 __global__ void __launch_bounds__(256)
-k_wcolsum(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w, int64_t ws, int64_t M, int N,
+k_wcolsum(const T* __restrict__ X, int64_t ldx, const T* __restrict__ w, int64_t ws, int64_t M, int N,
           int64_t rows_per_block, float* __restrict__ out) {
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
     for (int n = threadIdx.x; n < N; n += blockDim.x) {
         float s = 0.f;
-        for (int64_t m = r0; m < r1; ++m) s += (w ? w[m * ws] : 1.0f) * X[m * ldx + n];
+        for (int64_t m = r0; m < r1; ++m) s += (w ? ldf(w + m * ws) : 1.0f) * ldf(X + m * ldx + n);
         atomicAdd(out + n, s);
     }
 }
@@ -217,9 +317,9 @@ k_wcolsum(const float* __restrict__ X, int64_t ldx, const float* __restrict__ w,
 // ----------------------------------------------------------------------------------------------------------
 enum Act { kActNone = 0, kActSigmoid = 1, kActRelu = 2 };
 
-template <int NMAX>
+template <int NMAX, class T>
 __global__ void __launch_bounds__(256)
-k_rowdot(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw, const float* __restrict__ b,
+k_rowdot(const T* __restrict__ A, int64_t lda, const float* __restrict__ W, int64_t ldw, const float* __restrict__ b,
          int64_t M, int N, int K, int act, float* __restrict__ out, int64_t ldo) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t m = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -227,9 +327,9 @@ k_rowdot(const float* __restrict__ A, int64_t lda, const float* __restrict__ W, 
     float s[NMAX];
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) s[n] = 0.f;
-    const float* a = A + m * lda;
+    const T* a = A + m * lda;
     for (int k = lane; k < K; k += 32) {
-        const float av = a[k];
+        const float av = ldf(a + k);
 #pragma unroll
         for (int n = 0; n < NMAX; ++n)
             if (n < N) s[n] = fmaf(av, __ldg(W + n * ldw + k), s[n]);
@@ -255,10 +355,10 @@ __device__ __forceinline__ float act_grad(int act, float y) {   // d act / d pre
 }
 
 // dA[m,k] = relu'(A[m,k]) * sum_n dpre[m,n] W[n,k],   dpre = d_out * act'(out)
-template <int NMAX>
+template <int NMAX, class T>
 __global__ void k_rowdot_dgrad(const float* __restrict__ d_out, const float* __restrict__ out, int64_t ldo, int act,
-                               const float* __restrict__ W, int64_t ldw, const float* __restrict__ A, int64_t lda,
-                               int64_t M, int N, int K, float* __restrict__ dA, int64_t ldda) {
+                               const float* __restrict__ W, int64_t ldw, const T* __restrict__ A, int64_t lda,
+                               int64_t M, int N, int K, T* __restrict__ dA, int64_t ldda) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * K) return;
     const int64_t m = i / K; const int k = (int)(i - m * K);
@@ -266,14 +366,14 @@ __global__ void k_rowdot_dgrad(const float* __restrict__ d_out, const float* __r
 #pragma unroll
     for (int n = 0; n < NMAX; ++n)
         if (n < N) s = fmaf(d_out[m * ldo + n] * act_grad(act, out[m * ldo + n]), __ldg(W + n * ldw + k), s);
-    dA[m * ldda + k] = A[m * lda + k] > 0.f ? s : 0.f;
+    stf(dA + m * ldda + k, ldf(A + m * lda + k) > 0.f ? s : 0.f);
 }
 
 // dW[n,k] += sum_m dpre[m,n] A[m,k];  db[n] += sum_m dpre[m,n]
-template <int NMAX>
+template <int NMAX, class T>
 __global__ void __launch_bounds__(256)
 k_rowdot_wgrad(const float* __restrict__ d_out, const float* __restrict__ out, int64_t ldo, int act,
-               const float* __restrict__ A, int64_t lda, int64_t M, int N, int K, int64_t rows_per_block,
+               const T* __restrict__ A, int64_t lda, int64_t M, int N, int K, int64_t rows_per_block,
                float* __restrict__ dW, int64_t ldw, float* __restrict__ db) {
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t r1 = (r0 + rows_per_block < M) ? r0 + rows_per_block : M;
@@ -282,7 +382,7 @@ k_rowdot_wgrad(const float* __restrict__ d_out, const float* __restrict__ out, i
 #pragma unroll
         for (int n = 0; n < NMAX; ++n) s[n] = 0.f;
         for (int64_t m = r0; m < r1; ++m) {
-            const float av = (k < K) ? A[m * lda + k] : 1.0f;
+            const float av = (k < K) ? ldf(A + m * lda + k) : 1.0f;
 #pragma unroll
             for (int n = 0; n < NMAX; ++n)
                 if (n < N) s[n] = fmaf(d_out[m * ldo + n] * act_grad(act, out[m * ldo + n]), av, s[n]);
@@ -296,124 +396,174 @@ k_rowdot_wgrad(const float* __restrict__ d_out, const float* __restrict__ out, i
 }
 
 // ----------------------------------------------------------------------------------------------------------
-// GEMM epilogues
+// GEMM epilogues.  Each provides run<W>(m, n, v, nv): W consecutive columns n..n+W-1 of row m, the first nv of
+// them inside the GEMM's N; operator() overloads adapt to the SIMT engine (W = 4) and the tcgen05 engine (W = 8).
 // ----------------------------------------------------------------------------------------------------------
-struct EpiFwdAct {   // out[m,n] = softplus100(acc + b[n]) * oscale
-    const float* bias; float* out; int64_t ldo; float oscale;
+template <class Derived>
+struct EpiBase {
+    int N;   // real number of output columns (the tcgen05 engine runs on a padded N)
     __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
-        float* o = out + m * ldo + n;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nv) o[j] = softplus100(v[j] + __ldg(bias + n + j)) * oscale;
+        static_cast<const Derived*>(this)->template run<4>(m, n, v, nv);
+    }
+    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[8]) const {
+        const int nv = N - n;
+        if (nv > 0) static_cast<const Derived*>(this)->template run<8>(m, n, v, nv < 8 ? nv : 8);
     }
 };
-struct EpiBias {     // out[m,n] = acc + b[n]
-    const float* bias; float* out; int64_t ldo;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
-        float* o = out + m * ldo + n;
+
+template <class T>
+struct EpiFwdAct : EpiBase<EpiFwdAct<T>> {   // out[m,n] = softplus100(acc + b[n]) * oscale
+    const float* bias; T* out; int64_t ldo; float oscale;
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        float o[W];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nv) o[j] = v[j] + __ldg(bias + n + j);
+        for (int j = 0; j < W; ++j) o[j] = j < nv ? softplus100<kIsBf16<T>>(v[j] + __ldg(bias + n + j)) * oscale : 0.f;
+        store_row<W>(out + m * ldo + n, o, nv);
     }
 };
-struct EpiRelu {     // out[m,n] = relu(acc + b[n])
-    const float* bias; float* out; int64_t ldo;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
-        float* o = out + m * ldo + n;
+template <class T>
+struct EpiBias : EpiBase<EpiBias<T>> {       // out[m,n] = acc + b[n]
+    const float* bias; T* out; int64_t ldo;
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        float o[W];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nv) o[j] = fmaxf(v[j] + __ldg(bias + n + j), 0.f);
+        for (int j = 0; j < W; ++j) o[j] = j < nv ? v[j] + __ldg(bias + n + j) : 0.f;
+        store_row<W>(out + m * ldo + n, o, nv);
     }
 };
-struct EpiAtomic {   // C[m,n] += acc   (split-K weight gradients)
-    float* C; int64_t ldc;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
-        float* o = C + m * ldc + n;
+template <class T>
+struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
+    const float* bias; T* out; int64_t ldo;
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        float o[W];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < W; ++j) o[j] = j < nv ? fmaxf(v[j] + __ldg(bias + n + j), 0.f) : 0.f;
+        store_row<W>(out + m * ldo + n, o, nv);
+    }
+};
+// C[row(m), n] += acc  (split-K weight gradients).  With perm_rows > 0 the GEMM's row index i addresses the
+// permuted last layer [features..., sdf]: i < perm_rows - 1 -> row i + 1, i == perm_rows - 1 -> row 0.
+struct EpiAtomic : EpiBase<EpiAtomic> {
+    float* C; int64_t ldc; int Mrows; int perm_rows;
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        if (m >= Mrows) return;
+        const int64_t r = perm_rows > 0 ? (m == perm_rows - 1 ? 0 : m + 1) : m;
+        float* o = C + r * ldc + n;
+#pragma unroll
+        for (int j = 0; j < W; ++j)
             if (j < nv) atomicAdd(o + j, v[j]);
     }
 };
 // reverse sweep, layer l: acc = (a_l W_l)[m,n], n over the layer's inputs
-struct EpiRev {
-    const float* Hin; int64_t ldh; float hscale;   // stored input of layer l and the factor that undoes its scaling
-    float* Aout; int64_t lda;                      // a_{l-1}
+template <class T>
+struct EpiRev : EpiBase<EpiRev<T>> {
+    const T* Hin; int64_t ldh; float hscale;       // stored input of layer l and the factor that undoes its scaling
+    T* Aout; int64_t lda;                          // a_{l-1}
     float* g0; int64_t ldg;
     int dh; float qscale;                          // skip layer: columns >= dh are the h0 half; both halves scaled 1/sqrt2
     int layer0, g0_accum;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        if (!layer0 && n + nv <= dh) {             // fast path: a whole group of hidden columns
+            float h[W], o[W];
+            load_row<W>(Hin + m * ldh + n, h, nv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < W; ++j) o[j] = v[j] * qscale * sig_from_h<kIsBf16<T>>(h[j] * hscale);
+            store_row<W>(Aout + m * lda + n, o, nv);
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
             if (j >= nv) break;
             const int c = n + j;
             const float r = v[j] * qscale;
             if (c >= dh) { g0[m * ldg + (c - dh)] = r; continue; }
             if (layer0) { float* g = g0 + m * ldg + c; *g = g0_accum ? *g + r : r; }
-            else Aout[m * lda + c] = r * sig_from_h(Hin[m * ldh + c] * hscale);
+            else stf(Aout + m * lda + c, r * sig_from_h<kIsBf16<T>>(ldf(Hin + m * ldh + c) * hscale));
         }
     }
 };
 // tangent sweep, layer l: acc = (t_l W_l^T)[m,n], n over the layer's outputs
-struct EpiTan {
-    const float* Hn; int64_t ldh; float hscale;    // h_{l+1} as stored (input of layer l+1)
-    float* AZ; int64_t lda;                        // in: a_l, out: z_l
-    float* Tout; int64_t ldt; float tscale;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
+template <class T>
+struct EpiTan : EpiBase<EpiTan<T>> {
+    const T* Hn; int64_t ldh; float hscale;        // h_{l+1} as stored (input of layer l+1)
+    T* AZ; int64_t lda;                            // in: a_l, out: z_l
+    T* Tout; int64_t ldt; float tscale;
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        float h[W], a[W], t[W], z[W];
+        load_row<W>(Hn + m * ldh + n, h, nv);
+        load_row<W>(AZ + m * lda + n, a, nv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (j >= nv) break;
-            const float h = Hn[m * ldh + n + j] * hscale;
-            const float s = sig_from_h(h);
-            Tout[m * ldt + n + j] = v[j] * s * tscale;
-            float* az = AZ + m * lda + n + j;
-            *az = v[j] * (*az) * dsig_over_sig_from_h(h);
+        for (int j = 0; j < W; ++j) {
+            float s, d;
+            sig_dsig_from_h<kIsBf16<T>>(h[j] * hscale, s, d);
+            t[j] = v[j] * s * tscale;
+            z[j] = v[j] * a[j] * d;
         }
+        store_row<W>(Tout + m * ldt + n, t, nv);
+        store_row<W>(AZ + m * lda + n, z, nv);
     }
 };
 // backward sweep, layer l: acc = (pbar_l W_l)[m,n], n over the layer's inputs
-struct EpiBwd {
-    const float* Hin; int64_t ldh; float hscale;
-    float* PZ; int64_t ldp;                        // in: z_{l-1}, out: pbar_{l-1}
+template <class T>
+struct EpiBwd : EpiBase<EpiBwd<T>> {
+    const T* Hin; int64_t ldh; float hscale;
+    T* PZ; int64_t ldp;                            // in: z_{l-1}, out: pbar_{l-1}
     float* bh0; int64_t ldb;                       // adjoint of h_0 (hash-grid nets only), may be null
     int dh; float qscale; int layer0, bh0_accum;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        if (!layer0 && n + nv <= dh) {
+            float h[W], z[W];
+            load_row<W>(Hin + m * ldh + n, h, nv);
+            load_row<W>(PZ + m * ldp + n, z, nv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < W; ++j) z[j] = v[j] * qscale * sig_from_h<kIsBf16<T>>(h[j] * hscale) + z[j];
+            store_row<W>(PZ + m * ldp + n, z, nv);
+            return;
+        }
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
             if (j >= nv) break;
             const int c = n + j;
             const float r = v[j] * qscale;
             if (c >= dh) { if (bh0) bh0[m * ldb + (c - dh)] = r; continue; }
             if (layer0) { if (bh0) { float* g = bh0 + m * ldb + c; *g = bh0_accum ? *g + r : r; } }
-            else { float* p = PZ + m * ldp + c; *p = r * sig_from_h(Hin[m * ldh + c] * hscale) + *p; }
+            else { T* p = PZ + m * ldp + c; stf(p, r * sig_from_h<kIsBf16<T>>(ldf(Hin + m * ldh + c) * hscale) + ldf(p)); }
         }
     }
 };
-struct EpiBwdRelu {  // colour net dgrad: out[m,n] = acc * [Hin[m,n] > 0]
-    const float* Hin; int64_t ldh; float* out; int64_t ldo;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
+template <class T>
+struct EpiBwdRelu : EpiBase<EpiBwdRelu<T>> {  // colour net dgrad: out[m,n] = acc * [Hin[m,n] > 0]
+    const T* Hin; int64_t ldh; T* out; int64_t ldo;
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        float h[W], o[W];
+        load_row<W>(Hin + m * ldh + n, h, nv);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (j < nv) out[m * ldo + n + j] = Hin[m * ldh + n + j] > 0.f ? v[j] : 0.f;
+        for (int j = 0; j < W; ++j) o[j] = h[j] > 0.f ? v[j] : 0.f;
+        store_row<W>(out + m * ldo + n, o, nv);
     }
 };
 // colour net layer-0 dgrad: route d(input) columns to the SDF net's adjoints
-struct EpiColorIn {
+template <class T>
+struct EpiColorIn : EpiBase<EpiColorIn<T>> {
+    int n_off;                                     // column offset of this launch (the tcgen05 engine splits N > 256)
     int nc, fc, F, cc, cd;                         // column of the normal (-1 = none), of feat, of the code
-    float* dn; float* Dout; int64_t ldo; float* dcode; int64_t ldc;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
+    float* dn; T* Dout; int64_t ldo; int feat_col0; float* dcode; int64_t ldc;
+    template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
+        const int c0 = n + n_off;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < W; ++j) {
             if (j >= nv) break;
-            const int c = n + j;
+            const int c = c0 + j;
             if (nc >= 0 && c >= nc && c < nc + 3) dn[3 * m + (c - nc)] = v[j];
-            else if (c >= fc && c < fc + F) Dout[m * ldo + 1 + (c - fc)] = v[j];
+            else if (c >= fc && c < fc + F) stf(Dout + m * ldo + feat_col0 + (c - fc), v[j]);
             else if (cd > 0 && c >= cc && c < cc + cd) dcode[m * ldc + (c - cc)] = v[j];
         }
     }
 };
 
 // reverse-sweep start: a_{L-1} = e_0, so (a W_{L-1})[m,n] = W_{L-1}[0,n] for every point
-__global__ void k_rev_init(const float* __restrict__ w_row, int64_t M, int N, EpiRev epi) {
+template <class T>
+__global__ void k_rev_init(const float* __restrict__ w_row, int64_t M, int N, EpiRev<T> epi) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int n4 = (N + 3) / 4;
     if (i >= M * n4) return;
@@ -421,22 +571,25 @@ __global__ void k_rev_init(const float* __restrict__ w_row, int64_t M, int N, Ep
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = (n + j < N) ? __ldg(w_row + n + j) : 0.f;
-    epi(m, n, v, (N - n) < 4 ? (N - n) : 4);
+    epi.template run<4>(m, n, v, (N - n) < 4 ? (N - n) : 4);
 }
 
 // colour-net input row (network.py:393-413): idr [x, PE(view), normal, feat, code], nerf [PE(view), feat, code].
-// The feat columns are written by the SDF net's last layer; this kernel fills the rest.
+// The feat columns are written by the SDF net's last layer; this kernel fills the rest (and the zero padding).
+template <class T>
 __global__ void k_color_input(const float* __restrict__ x, const float* __restrict__ view, const float* __restrict__ normal,
                               const float* __restrict__ code, int64_t M, int n_samples, int mode_idr, int pe_w, int F, int cd,
-                              int code_per_ray, float* __restrict__ X, int64_t ldx) {
+                              int code_per_ray, T* __restrict__ X, int64_t ldx, int pad_cols) {
     const int pre = (mode_idr ? 3 : 0) + pe_w + (mode_idr ? 3 : 0);
-    const int cols = pre + cd;
+    const int cols = pre + cd + pad_cols;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= M * cols) return;
     const int64_t m = i / cols; int j = (int)(i - m * cols);
     const int64_t ray = m / n_samples;
     float v; int col;
-    if (j >= pre) {
+    if (j >= pre + cd) {
+        v = 0.f; col = pre + F + cd + (j - pre - cd);
+    } else if (j >= pre) {
         v = code[(code_per_ray ? ray : 0) * cd + (j - pre)];
         col = pre + F + (j - pre);
     } else {
@@ -448,7 +601,7 @@ __global__ void k_color_input(const float* __restrict__ x, const float* __restri
             else v = normal[3 * m + (j - pe_w)];
         }
     }
-    X[m * ldx + col] = v;
+    stf(X + m * ldx + col, v);
 }
 
 __global__ void k_ray_points(const float* __restrict__ o, const float* __restrict__ d, const float* __restrict__ z,
@@ -470,6 +623,26 @@ __global__ void k_code_grad(const float* __restrict__ dcode, int64_t n_rays, int
     out[i] += s;
 }
 
+// bf16 weight preparation for the tensor-core path.  Wk[r, k] = W[row(r), k] (zero padded to [rows_p, in_p]),
+// Wt[k, r] = W[row(r), k] (zero padded to [in_p16, rows_p64]); row(r) applies the [features..., sdf] permutation.
+__global__ void k_prep_weights(const float* __restrict__ W, int64_t ldw, int out, int in, int perm, bf16* __restrict__ Wk,
+                               int wk_rows, int wk_ld, bf16* __restrict__ Wt, int wt_rows, int wt_ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nk = (int64_t)wk_rows * wk_ld, nt = (int64_t)wt_rows * wt_ld;
+    if (i < nk) {
+        const int r = (int)(i / wk_ld), k = (int)(i - (int64_t)r * wk_ld);
+        float v = 0.f;
+        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + k]; }
+        Wk[i] = __float2bfloat16(v);
+    } else if (i < nk + nt) {
+        const int64_t t = i - nk;
+        const int k = (int)(t / wt_ld), r = (int)(t - (int64_t)k * wt_ld);
+        float v = 0.f;
+        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + k]; }
+        Wt[t] = __float2bfloat16(v);
+    }
+}
+
 inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)msdf_div_up(n, t); }
 
 #define RUN(expr) do { int rc_ = (expr); if (rc_) return rc_; } while (0)
@@ -478,7 +651,7 @@ inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)msdf_div_up(n, t
 // ----------------------------------------------------------------------------------------------------------
 // workspace layout for one chunk
 // ----------------------------------------------------------------------------------------------------------
-struct ColorGeom { int pe_w, nc, fc, cc, in0, ldx; };
+struct ColorGeom { int pe_w, nc, fc, cc, in0; };
 
 ColorGeom color_geom(const msdf_color_desc* cd) {
     ColorGeom g;
@@ -486,88 +659,29 @@ ColorGeom color_geom(const msdf_color_desc* cd) {
     if (cd->mode_idr) { g.nc = 3 + g.pe_w; g.fc = g.nc + 3; } else { g.nc = -1; g.fc = g.pe_w; }
     g.cc = g.fc + cd->feat_dim;
     g.in0 = g.cc + cd->code_dim;
-    g.ldx = round4(g.in0);
     return g;
 }
 
+template <class T>
 struct Bufs {
-    float* H[MSDF_MAX_LAYERS];   // H[0] = encoded input (ld d0p); H[l] = input of layer l (ld ldh)
-    float* A[MSDF_MAX_LAYERS];   // a_l, later z_l / pbar_l  (l < L-1)
-    float *G0, *TG0, *BH0, *T[2], *Dout, *dydx, *sdf_raw, *mask, *dn, *dn_color, *gradc, *sdfc;
-    float* X; float* C[MSDF_MAX_LAYERS]; float* dC[2]; float* dcode; float* rgbc;
-    int64_t ldo;
+    T* H[MSDF_MAX_LAYERS];   // H[0] = encoded input (ld d0p); H[l] = input of layer l (ld ldh)
+    T* A[MSDF_MAX_LAYERS];   // a_l, later z_l / pbar_l  (l < L-1)
+    T *TG0, *T2[2], *Dout;
+    float *G0, *BH0, *dydx, *hashf, *sdf_raw, *mask, *dn, *dn_color, *gradc, *sdfc, *dcode;
+    T* X; T* C[MSDF_MAX_LAYERS]; T* dC[2];
+    int64_t d0p, ldh, ldo, ldx, ldc;   // leading dimensions
 };
 
 struct Carver {
     char* base; size_t off; bool dry;
-    float* take(int64_t rows, int64_t cols) {
-        const size_t bytes = msdf_align((size_t)rows * (size_t)cols * sizeof(float));
-        float* p = dry ? nullptr : reinterpret_cast<float*>(base + off);
+    template <class U> U* take(int64_t rows, int64_t cols) {
+        const size_t bytes = msdf_align((size_t)rows * (size_t)cols * sizeof(U), 1024);
+        U* p = dry ? nullptr : reinterpret_cast<U*>(base + off);
         off += bytes;
         return p;
     }
 };
 
-// mode: MSDF_MODE_*
-size_t carve(const Net& sn, const msdf_encoding_desc* enc, const Net* cn, const msdf_color_desc* cdesc, int64_t Mc, int mode,
-             void* ws, Bufs* out) {
-    Carver c{(char*)ws, 0, ws == nullptr};
-    Bufs b{};
-    const bool grid = enc->grid_feat_dim > 0 && enc->table != nullptr;
-    b.H[0] = c.take(Mc, sn.d0p);
-    b.sdf_raw = c.take(Mc, 1);
-    if (mode == MSDF_MODE_SDF_ONLY) {
-        float* pp[2] = {c.take(Mc, sn.ldh), c.take(Mc, sn.ldh)};
-        for (int l = 1; l < sn.L; ++l) b.H[l] = pp[(l - 1) & 1];
-    } else {
-        for (int l = 1; l < sn.L; ++l) b.H[l] = c.take(Mc, sn.ldh);
-        if (mode == MSDF_MODE_FORWARD) {
-            float* pp[2] = {c.take(Mc, sn.ldh), c.take(Mc, sn.ldh)};
-            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = pp[l & 1];
-        } else {
-            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = c.take(Mc, sn.ldh);
-        }
-        b.G0 = c.take(Mc, sn.d0p);
-        if (grid) b.dydx = c.take(Mc, enc->n_levels * 3 * enc->level_dim);
-        b.mask = c.take(Mc, 1);
-        if (mode == MSDF_MODE_BACKWARD) {
-            b.TG0 = c.take(Mc, sn.d0p);
-            if (grid) b.BH0 = c.take(Mc, sn.d0p);
-            b.T[0] = c.take(Mc, sn.ldh); b.T[1] = c.take(Mc, sn.ldh);
-            b.ldo = round4(sn.out[sn.L - 1]);
-            b.Dout = c.take(Mc, b.ldo);
-            b.dn = c.take(Mc, 3); b.dn_color = c.take(Mc, 3);
-            b.gradc = c.take(Mc, 3); b.sdfc = c.take(Mc, 1);
-        }
-        if (cn != nullptr) {
-            const ColorGeom g = color_geom(cdesc);
-            b.X = c.take(Mc, g.ldx);
-            b.C[0] = b.X;
-            for (int l = 1; l < cn->L; ++l) b.C[l] = c.take(Mc, cn->ldh);
-            if (mode == MSDF_MODE_BACKWARD) {
-                b.dC[0] = c.take(Mc, cn->ldh); b.dC[1] = c.take(Mc, cn->ldh);
-                if (cdesc->code_dim > 0) b.dcode = c.take(Mc, cdesc->code_dim);
-            }
-        }
-    }
-    if (out) *out = b;
-    return c.off;
-}
-
-int64_t pick_chunk(const Net& sn, const msdf_encoding_desc* enc, const Net* cn, const msdf_color_desc* cd, int64_t M, int mode,
-                   size_t ws_bytes) {
-    int64_t cap = 65536;
-    if (mode == MSDF_MODE_SDF_ONLY) cap = 262144;
-    int64_t mc = M < cap ? M : cap;
-    mc = (mc + 127) / 128 * 128;
-    while (mc > 128 && carve(sn, enc, cn, cd, mc, mode, nullptr, nullptr) > ws_bytes) mc = (mc / 2 + 127) / 128 * 128;
-    if (carve(sn, enc, cn, cd, mc, mode, nullptr, nullptr) > ws_bytes) return 0;
-    return mc;
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// sweeps over one chunk
-// ----------------------------------------------------------------------------------------------------------
 struct Ctx {
     Net sn; const msdf_encoding_desc* enc; bool grid; int pe_w; float hash_chain;
     bool has_color; Net cn; const msdf_color_desc* cd; ColorGeom cg;
@@ -575,201 +689,370 @@ struct Ctx {
     cudaStream_t st;
 };
 
+// mode: MSDF_MODE_*.  sn_w / cn_w (may be null) receive the bf16 weight-copy pointers.
+template <class T>
+size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* sn_w, Net* cn_w) {
+    const Net& sn = cx.sn;
+    const msdf_encoding_desc* enc = cx.enc;
+    Carver c{(char*)ws, 0, ws == nullptr};
+    Bufs<T> b{};
+    if (kIsBf16<T>) {   // weight copies first (fixed size, independent of the chunk)
+        Net* dst[2] = {sn_w, cn_w};
+        const Net* src[2] = {&cx.sn, &cx.cn};
+        for (int k = 0; k < (cx.has_color ? 2 : 1); ++k)
+            for (int l = 0; l < src[k]->L; ++l) {
+                bf16* wk = c.take<bf16>(round_up(src[k]->out[l], 16), round_up(src[k]->in[l], 64));
+                bf16* wt = c.take<bf16>(round_up(src[k]->in[l], 16), round_up(src[k]->out[l], 64));
+                if (dst[k]) { dst[k]->Wk[l] = wk; dst[k]->Wt[l] = wt; }
+            }
+    }
+    const bool grid_feats = enc->grid_feat_dim > 0 && enc->table != nullptr;
+    b.d0p = padw<T>(sn.d0); b.ldh = padw<T>(sn.maxw);
+    b.H[0] = c.take<T>(Mc, b.d0p);
+    b.sdf_raw = c.take<float>(Mc, 1);
+    if (grid_feats && kIsBf16<T>) b.hashf = c.take<float>(Mc, enc->grid_feat_dim);
+    if (mode == MSDF_MODE_SDF_ONLY) {
+        T* pp[2] = {c.take<T>(Mc, b.ldh), c.take<T>(Mc, b.ldh)};
+        for (int l = 1; l < sn.L; ++l) b.H[l] = pp[(l - 1) & 1];
+    } else {
+        for (int l = 1; l < sn.L; ++l) b.H[l] = c.take<T>(Mc, b.ldh);
+        if (mode == MSDF_MODE_FORWARD) {
+            T* pp[2] = {c.take<T>(Mc, b.ldh), c.take<T>(Mc, b.ldh)};
+            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = pp[l & 1];
+        } else {
+            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = c.take<T>(Mc, b.ldh);
+        }
+        b.G0 = c.take<float>(Mc, round_up(sn.d0, 4));
+        if (grid_feats) b.dydx = c.take<float>(Mc, enc->n_levels * 3 * enc->level_dim);
+        b.mask = c.take<float>(Mc, 1);
+        if (mode == MSDF_MODE_BACKWARD) {
+            b.TG0 = c.take<T>(Mc, b.d0p);
+            if (grid_feats) b.BH0 = c.take<float>(Mc, round_up(sn.d0, 4));
+            b.T2[0] = c.take<T>(Mc, b.ldh); b.T2[1] = c.take<T>(Mc, b.ldh);
+            b.ldo = padw<T>(sn.out[sn.L - 1]);
+            b.Dout = c.take<T>(Mc, b.ldo);
+            b.dn = c.take<float>(Mc, 3); b.dn_color = c.take<float>(Mc, 3);
+            b.gradc = c.take<float>(Mc, 3); b.sdfc = c.take<float>(Mc, 1);
+        }
+        if (cx.has_color) {
+            b.ldx = padw<T>(cx.cg.in0); b.ldc = padw<T>(cx.cn.maxw);
+            b.X = c.take<T>(Mc, b.ldx);
+            b.C[0] = b.X;
+            for (int l = 1; l < cx.cn.L; ++l) b.C[l] = c.take<T>(Mc, b.ldc);
+            if (mode == MSDF_MODE_BACKWARD) {
+                b.dC[0] = c.take<T>(Mc, b.ldc); b.dC[1] = c.take<T>(Mc, b.ldc);
+                if (cx.cd->code_dim > 0) b.dcode = c.take<float>(Mc, cx.cd->code_dim);
+            }
+        }
+    }
+    if (out) *out = b;
+    return c.off;
+}
+
+template <class T>
+int64_t pick_chunk(const Ctx& cx, int64_t M, int mode, size_t ws_bytes) {
+    int64_t cap = kIsBf16<T> ? 262144 : 65536;
+    if (mode == MSDF_MODE_SDF_ONLY) cap = 524288;
+    int64_t mc = M < cap ? M : cap;
+    mc = (mc + 127) / 128 * 128;
+    while (mc > 128 && carve<T>(cx, mc, mode, nullptr, nullptr, nullptr, nullptr) > ws_bytes) mc = (mc / 2 + 127) / 128 * 128;
+    if (carve<T>(cx, mc, mode, nullptr, nullptr, nullptr, nullptr) > ws_bytes) return 0;
+    return mc;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// GEMM back ends
+// ----------------------------------------------------------------------------------------------------------
+// C = epi(A W_l^T) over output rows [r0, r0 + nrows) of W_l (in the bf16 copy's row order)
+template <class T, class Epi>
+int gemm_nt(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t Mc, int r0, int nrows, Epi epi, const char* what) {
+    epi.N = nrows;
+    if constexpr (kIsBf16<T>) {
+        const int kp = round_up(n.in[l], 64);
+        return msdf_tc::launch_gemm(A, lda, Mc, kp, n.Wk[l] + (int64_t)r0 * kp, kp, round_up(nrows, 16), epi, c.st, what);
+    } else {
+        return msdf_gemm::launch<kNT>(A, lda, n.W[l] + (int64_t)r0 * n.ldw[l], n.ldw[l], Mc, nrows, n.in[l], 1, epi, c.st, what);
+    }
+}
+// C = epi(A W_l): A [Mc, out_l] -> [Mc, in_l]
+template <class T, class Epi>
+int gemm_nn(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t Mc, Epi epi, const char* what) {
+    epi.N = n.in[l];
+    if constexpr (kIsBf16<T>) {
+        const int kp = round_up(n.out[l], 64);
+        const int np = round_up(n.in[l], 16);
+        for (int c0 = 0; c0 < np; c0 += 256) {     // the accumulator holds at most 256 columns
+            const int bn = np - c0 < 256 ? np - c0 : 256;
+            Epi e = epi;
+            e.N = n.in[l] - c0;
+            if constexpr (std::is_same<Epi, EpiColorIn<T>>::value) e.n_off = c0;
+            else if (c0 > 0) { msdf_set_error("%s: more than 256 output columns", what); return MSDF_ERR_UNSUPPORTED; }
+            RUN(msdf_tc::launch_gemm(A, lda, Mc, kp, n.Wt[l] + (int64_t)c0 * kp, kp, bn, e, c.st, what));
+        }
+        return MSDF_OK;
+    } else {
+        return msdf_gemm::launch<kNN>(A, lda, n.W[l], n.ldw[l], Mc, n.in[l], n.out[l], 1, epi, c.st, what);
+    }
+}
+// dW[rows, cols] += X^T Y, X [Mc, rows], Y [Mc, cols]
+template <class T>
+int wgrad(const Ctx& c, const T* X, int64_t ldx, const T* Y, int64_t ldy, int rows, int cols, int64_t Mc, float* dW, int64_t ldw,
+          int perm_rows) {
+    EpiAtomic e{};
+    e.N = cols; e.C = dW; e.ldc = ldw; e.Mrows = rows; e.perm_rows = perm_rows;
+    if constexpr (kIsBf16<T>) {
+        return msdf_tc::launch_wgrad(X, ldx, round_up(rows, 64), Y, ldy, round_up(cols, 64), Mc, e, c.st, "weight gradient");
+    } else {
+        const int tiles = (int)(msdf_div_up(rows, msdf_gemm::BM) * msdf_div_up(cols, msdf_gemm::BN));
+        int splits = (int)((2 * 148 + tiles - 1) / tiles);
+        const int64_t max_splits = msdf_div_up(Mc, 512);
+        if (splits > max_splits) splits = (int)max_splits;
+        return msdf_gemm::launch<kTN>(X, ldx, Y, ldy, rows, cols, Mc, splits, e, c.st, "weight gradient");
+    }
+}
+template <class T>
+int colsum(const Ctx& c, const T* X, int64_t ldx, const T* w, int64_t ws, int64_t Mc, int N, float* out) {
+    const int64_t rpb = 256;
+    k_wcolsum<T><<<nblk(Mc, (int)rpb), 256, 0, c.st>>>(X, ldx, w, ws, Mc, N, rpb, out);
+    LAUNCHED("column sum");
+    return MSDF_OK;
+}
+
+int prep_weights(const Ctx& c, Net& n, int perm_last) {
+    n.perm_last = perm_last;
+    for (int l = 0; l < n.L; ++l) {
+        const int perm = (perm_last && l == n.L - 1) ? 1 : 0;
+        const int wk_rows = round_up(n.out[l], 16), wk_ld = round_up(n.in[l], 64);
+        const int wt_rows = round_up(n.in[l], 16), wt_ld = round_up(n.out[l], 64);
+        const int64_t total = (int64_t)wk_rows * wk_ld + (int64_t)wt_rows * wt_ld;
+        k_prep_weights<<<nblk(total), 256, 0, c.st>>>(n.W[l], n.ldw[l], n.out[l], n.in[l], perm, n.Wk[l], wk_rows, wk_ld, n.Wt[l],
+                                                     wt_rows, wt_ld);
+        LAUNCHED("weight prep");
+    }
+    return MSDF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// sweeps over one chunk
+// ----------------------------------------------------------------------------------------------------------
 inline float in_scale(const Net& n, int l) { return l == n.skip ? kSqrt2 : 1.0f; }   // undoes the stored 1/sqrt2
 
-int encode_chunk(const Ctx& c, const Bufs& b, const float* x, int64_t Mc, bool want_dydx) {
-    k_encode<<<nblk(Mc * c.pe_w), 256, 0, c.st>>>(x, Mc, c.pe_w, b.H[0], c.sn.d0p);
-    LAUNCHED("encode");
-    if (c.enc->grid_feat_dim > 0) {
-        if (c.grid) {
-            RUN(msdf_hash_forward_rows(x, c.enc->table, c.enc->offsets, b.H[0] + c.pe_w, c.sn.d0p, Mc, c.enc->level_dim,
-                                       c.enc->n_levels, c.enc->log2_per_level_scale, (uint32_t)c.enc->base_res,
-                                       c.enc->divide_factor, want_dydx ? b.dydx : nullptr, c.st));
-        } else {   // use_grid_feature = False: zero features (network.py:251-252)
-            k_zero_cols<<<nblk(Mc * c.enc->grid_feat_dim), 256, 0, c.st>>>(b.H[0], c.sn.d0p, Mc, c.pe_w, c.enc->grid_feat_dim);
-            LAUNCHED("zero grid features");
-        }
+template <class T>
+int encode_chunk(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, bool want_dydx) {
+    const int gw = c.enc->grid_feat_dim;
+    if (c.grid) {
+        // fp32 mode: features go straight into H0's columns; bf16 mode: through an fp32 staging buffer
+        float* dst = kIsBf16<T> ? b.hashf : reinterpret_cast<float*>(b.H[0]) + c.pe_w;
+        const int64_t ld = kIsBf16<T> ? gw : b.d0p;
+        RUN(msdf_hash_forward_rows(x, c.enc->table, c.enc->offsets, dst, ld, Mc, c.enc->level_dim, c.enc->n_levels,
+                                   c.enc->log2_per_level_scale, (uint32_t)c.enc->base_res, c.enc->divide_factor,
+                                   want_dydx ? b.dydx : nullptr, c.st));
     }
+    if (c.grid && !kIsBf16<T>) {   // the hash kernel already wrote its columns; PE only
+        k_encode<T><<<nblk(Mc * c.pe_w), 256, 0, c.st>>>(x, Mc, c.pe_w, 0, nullptr, b.H[0], b.d0p, c.pe_w);
+    } else {                       // PE + staged hash features (or zero features) + zero padding
+        const int cols = (int)b.d0p;
+        k_encode<T><<<nblk(Mc * cols), 256, 0, c.st>>>(x, Mc, c.pe_w, gw, c.grid ? b.hashf : nullptr, b.H[0], b.d0p, cols);
+    }
+    LAUNCHED("encode");
     return MSDF_OK;
 }
 
-// forward sweep; feat (ld ldf) may be null
-int forward_sweep(const Ctx& c, const Bufs& b, int64_t Mc, float* feat, int64_t ldf) {
+// forward sweep; feat (ld ldf_) may be null
+template <class T>
+int forward_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc, T* feat, int64_t ldf_) {
     const Net& n = c.sn;
     for (int l = 0; l < n.L - 1; ++l) {
-        const int64_t ldin = l == 0 ? n.d0p : n.ldh;
+        const int64_t ldin = l == 0 ? b.d0p : b.ldh;
         if (l + 1 == n.skip) {
-            k_skip_copy<<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.H[0], n.d0p, b.H[l + 1], n.ldh, Mc, n.d0, n.out[l], kInvSqrt2);
+            k_skip_copy<T><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.H[0], b.d0p, b.H[l + 1], b.ldh, Mc, n.d0, n.out[l], kInvSqrt2);
             LAUNCHED("skip copy");
         }
-        EpiFwdAct e{n.b[l], b.H[l + 1], n.ldh, l + 1 == n.skip ? kInvSqrt2 : 1.0f};
-        RUN((launch<kNT>(b.H[l], ldin, n.W[l], n.ldw[l], Mc, n.out[l], n.in[l], 1, e, c.st, "sdf forward layer")));
+        EpiFwdAct<T> e{};
+        e.bias = n.b[l]; e.out = b.H[l + 1]; e.ldo = b.ldh; e.oscale = l + 1 == n.skip ? kInvSqrt2 : 1.0f;
+        RUN((gemm_nt<T>(c, n, l, b.H[l], ldin, Mc, 0, n.out[l], e, "sdf forward layer")));
     }
     const int l = n.L - 1;
-    k_rowdot<1><<<nblk(Mc, 8), 256, 0, c.st>>>(b.H[l], n.ldh, n.W[l], n.ldw[l], n.b[l], Mc, 1, n.in[l], kActNone, b.sdf_raw, 1);
+    k_rowdot<1, T><<<nblk(Mc, 8), 256, 0, c.st>>>(b.H[l], b.ldh, n.W[l], n.ldw[l], n.b[l], Mc, 1, n.in[l], kActNone, b.sdf_raw, 1);
     LAUNCHED("sdf head");
     if (feat != nullptr && n.out[l] > 1) {
-        EpiBias e{n.b[l] + 1, feat, ldf};
-        RUN((launch<kNT>(b.H[l], n.ldh, n.W[l] + n.ldw[l], n.ldw[l], Mc, n.out[l] - 1, n.in[l], 1, e, c.st, "feature head")));
+        EpiBias<T> e{};
+        e.bias = n.b[l] + 1; e.out = feat; e.ldo = ldf_;
+        // rows of the features: 1.. in W_l; 0.. in the permuted bf16 copy
+        RUN((gemm_nt<T>(c, n, l, b.H[l], b.ldh, Mc, kIsBf16<T> ? 0 : 1, n.out[l] - 1, e, "feature head")));
     }
     return MSDF_OK;
 }
 
-EpiRev make_rev(const Net& n, const Bufs& b, int l) {
-    EpiRev e{};
-    e.Hin = b.H[l]; e.ldh = l == 0 ? n.d0p : n.ldh; e.hscale = in_scale(n, l);
-    e.Aout = l > 0 ? b.A[l - 1] : nullptr; e.lda = n.ldh;
-    e.g0 = b.G0; e.ldg = n.d0p;
+template <class T>
+EpiRev<T> make_rev(const Net& n, const Bufs<T>& b, int l) {
+    EpiRev<T> e{};
+    e.N = n.in[l];
+    e.Hin = b.H[l]; e.ldh = l == 0 ? b.d0p : b.ldh; e.hscale = in_scale(n, l);
+    e.Aout = l > 0 ? b.A[l - 1] : nullptr; e.lda = b.ldh;
+    e.g0 = b.G0; e.ldg = round_up(n.d0, 4);
     e.dh = l == n.skip ? n.in[l] - n.d0 : n.in[l];
     e.qscale = l == n.skip ? kInvSqrt2 : 1.0f;
     e.layer0 = l == 0; e.g0_accum = n.skip > 0;
     return e;
 }
 
-int reverse_sweep(const Ctx& c, const Bufs& b, int64_t Mc) {
+template <class T>
+int reverse_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc) {
     const Net& n = c.sn;
     {
         const int l = n.L - 1;
         const int n4 = (n.in[l] + 3) / 4;
-        k_rev_init<<<nblk(Mc * n4), 256, 0, c.st>>>(n.W[l], Mc, n.in[l], make_rev(n, b, l));
+        k_rev_init<T><<<nblk(Mc * n4), 256, 0, c.st>>>(n.W[l], Mc, n.in[l], make_rev<T>(n, b, l));
         LAUNCHED("reverse init");
     }
-    for (int l = n.L - 2; l >= 0; --l)
-        RUN((launch<kNN>(b.A[l], n.ldh, n.W[l], n.ldw[l], Mc, n.in[l], n.out[l], 1, make_rev(n, b, l), c.st, "sdf reverse layer")));
+    for (int l = n.L - 2; l >= 0; --l) {
+        if (kIsBf16<T> && n.out[l] % 64 != 0) {   // K padding of the operand must be finite (zero)
+            const int w = round_up(n.out[l], 64) - n.out[l];
+            k_zero_cols<T><<<nblk(Mc * w), 256, 0, c.st>>>(b.A[l], b.ldh, Mc, n.out[l], w);
+            LAUNCHED("zero operand padding");
+        }
+        RUN((gemm_nn<T>(c, n, l, b.A[l], b.ldh, Mc, make_rev<T>(n, b, l), "sdf reverse layer")));
+    }
     return MSDF_OK;
 }
 
-int decode_chunk(const Ctx& c, const Bufs& b, const float* x, int64_t Mc, bool with_grad, float* sdf, float* grad, float* mask) {
-    k_decode<<<nblk(Mc, 128), 128, 0, c.st>>>(x, with_grad ? b.G0 : nullptr, c.sn.d0p, Mc, c.pe_w, c.grid ? c.enc->grid_feat_dim : 0,
-                                             c.enc->n_levels, c.enc->level_dim, b.dydx, c.hash_chain, b.sdf_raw, c.clamp_radius,
-                                             c.sphere_scale, sdf, grad, mask);
+template <class T>
+int decode_chunk(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, bool with_grad, float* sdf, float* grad, float* mask) {
+    k_decode<<<nblk(Mc, 128), 128, 0, c.st>>>(x, with_grad ? b.G0 : nullptr, round_up(c.sn.d0, 4), Mc, c.pe_w,
+                                             c.grid ? c.enc->grid_feat_dim : 0, c.enc->n_levels, c.enc->level_dim, b.dydx, c.hash_chain,
+                                             b.sdf_raw, c.clamp_radius, c.sphere_scale, sdf, grad, mask);
     LAUNCHED("decode");
     return MSDF_OK;
 }
 
-int color_forward(const Ctx& c, const Bufs& b, const float* x, int64_t Mc, const float* view, int n_samples,
+template <class T>
+int color_forward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, const float* view, int n_samples,
                   const float* code, const float* normal, float* rgb) {
     const Net& n = c.cn;
     const ColorGeom& g = c.cg;
-    const int cols = g.in0 - c.cd->feat_dim;
+    const int pad = (int)b.ldx - g.in0;
+    const int cols = g.in0 - c.cd->feat_dim + pad;
     // chunks start on a ray boundary; view / code pointers are already offset to the chunk's first ray
-    k_color_input<<<nblk(Mc * cols), 256, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, g.pe_w, c.cd->feat_dim,
-                                                    c.cd->code_dim, c.cd->code_per_ray, b.X, g.ldx);
+    k_color_input<T><<<nblk(Mc * cols), 256, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, g.pe_w, c.cd->feat_dim,
+                                                       c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, pad);
     LAUNCHED("colour input");
     for (int l = 0; l < n.L - 1; ++l) {
-        EpiRelu e{n.b[l], b.C[l + 1], n.ldh};
-        RUN((launch<kNT>(b.C[l], l == 0 ? g.ldx : n.ldh, n.W[l], n.ldw[l], Mc, n.out[l], n.in[l], 1, e, c.st, "colour layer")));
+        EpiRelu<T> e{};
+        e.bias = n.b[l]; e.out = b.C[l + 1]; e.ldo = b.ldc;
+        RUN((gemm_nt<T>(c, n, l, b.C[l], l == 0 ? b.ldx : b.ldc, Mc, 0, n.out[l], e, "colour layer")));
     }
     const int l = n.L - 1;
     MSDF_CHECK_ARG(n.out[l] <= 4, "colour net: d_out=%d > 4 unsupported", n.out[l]);
     if (rgb == nullptr) return MSDF_OK;   // backward recompute: the saved rgb drives act', the head is not needed
-    k_rowdot<4><<<nblk(Mc, 8), 256, 0, c.st>>>(b.C[l], n.ldh, n.W[l], n.ldw[l], n.b[l], Mc, n.out[l], n.in[l],
-                                              c.cd->final_act == 0 ? kActSigmoid : kActRelu, rgb, n.out[l]);
+    k_rowdot<4, T><<<nblk(Mc, 8), 256, 0, c.st>>>(b.C[l], b.ldc, n.W[l], n.ldw[l], n.b[l], Mc, n.out[l], n.in[l],
+                                                 c.cd->final_act == 0 ? kActSigmoid : kActRelu, rgb, n.out[l]);
     LAUNCHED("colour head");
     return MSDF_OK;
 }
 
-int wgrad(const float* X, int64_t ldx, const float* Y, int64_t ldy, int rows, int cols, int64_t Mc, float* dW, int64_t ldw,
-          cudaStream_t st) {
-    const int tiles = (int)(msdf_div_up(rows, BM) * msdf_div_up(cols, BN));
-    int splits = (int)((2 * 148 + tiles - 1) / tiles);
-    const int64_t max_splits = msdf_div_up(Mc, 512);
-    if (splits > max_splits) splits = (int)max_splits;
-    EpiAtomic e{dW, ldw};
-    return launch<kTN>(X, ldx, Y, ldy, rows, cols, Mc, splits, e, st, "weight gradient");
-}
-
-int colsum(const float* X, int64_t ldx, const float* w, int64_t ws, int64_t Mc, int N, float* out, cudaStream_t st) {
-    const int64_t rpb = 256;
-    k_wcolsum<<<nblk(Mc, (int)rpb), 256, 0, st>>>(X, ldx, w, ws, Mc, N, rpb, out);
-    LAUNCHED("column sum");
-    return MSDF_OK;
-}
-
-int color_backward(const Ctx& c, const Bufs& b, int64_t Mc, const float* rgb, const float* d_rgb, const msdf_mlp_grads* gr) {
+template <class T>
+int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb, const float* d_rgb, const msdf_mlp_grads* gr) {
     const Net& n = c.cn;
     const ColorGeom& g = c.cg;
     int l = n.L - 1;
     const int act = c.cd->final_act == 0 ? kActSigmoid : kActRelu;
-    k_rowdot_wgrad<4><<<nblk(Mc, 512), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, b.C[l], n.ldh, Mc, n.out[l], n.in[l], 512,
-                                                      gr->dW[l], n.ldw[l], gr->db[l]);
+    k_rowdot_wgrad<4, T><<<nblk(Mc, 512), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, b.C[l], b.ldc, Mc, n.out[l], n.in[l], 512,
+                                                         gr->dW[l], n.ldw[l], gr->db[l]);
     LAUNCHED("colour head wgrad");
-    float* P = b.dC[0];
-    k_rowdot_dgrad<4><<<nblk(Mc * n.in[l]), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, n.W[l], n.ldw[l], b.C[l], n.ldh, Mc,
-                                                           n.out[l], n.in[l], P, n.ldh);
+    T* P = b.dC[0];
+    k_rowdot_dgrad<4, T><<<nblk(Mc * n.in[l]), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, n.W[l], n.ldw[l], b.C[l], b.ldc, Mc,
+                                                              n.out[l], n.in[l], P, b.ldc);
     LAUNCHED("colour head dgrad");
     int pp = 0;
     for (l = n.L - 2; l >= 0; --l) {
-        const int64_t ldin = l == 0 ? g.ldx : n.ldh;
-        RUN(wgrad(P, n.ldh, b.C[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], c.st));
-        RUN(colsum(P, n.ldh, nullptr, 0, Mc, n.out[l], gr->db[l], c.st));
+        const int64_t ldin = l == 0 ? b.ldx : b.ldc;
+        RUN(wgrad<T>(c, P, b.ldc, b.C[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+        RUN(colsum<T>(c, P, b.ldc, nullptr, 0, Mc, n.out[l], gr->db[l]));
         if (l > 0) {
-            float* Pn = b.dC[pp ^ 1];
-            EpiBwdRelu e{b.C[l], n.ldh, Pn, n.ldh};
-            RUN((launch<kNN>(P, n.ldh, n.W[l], n.ldw[l], Mc, n.in[l], n.out[l], 1, e, c.st, "colour dgrad")));
+            T* Pn = b.dC[pp ^ 1];
+            EpiBwdRelu<T> e{};
+            e.Hin = b.C[l]; e.ldh = b.ldc; e.out = Pn; e.ldo = b.ldc;
+            RUN((gemm_nn<T>(c, n, l, P, b.ldc, Mc, e, "colour dgrad")));
             P = Pn; pp ^= 1;
         } else {
-            EpiColorIn e{g.nc, g.fc, c.cd->feat_dim, g.cc, c.cd->code_dim, b.dn_color, b.Dout, b.ldo, b.dcode, c.cd->code_dim};
-            RUN((launch<kNN>(P, n.ldh, n.W[l], n.ldw[l], Mc, n.in[l], n.out[l], 1, e, c.st, "colour input dgrad")));
+            EpiColorIn<T> e{};
+            e.n_off = 0; e.nc = g.nc; e.fc = g.fc; e.F = c.cd->feat_dim; e.cc = g.cc; e.cd = c.cd->code_dim;
+            e.dn = b.dn_color; e.Dout = b.Dout; e.ldo = b.ldo; e.feat_col0 = kIsBf16<T> ? 0 : 1;
+            e.dcode = b.dcode; e.ldc = c.cd->code_dim;
+            RUN((gemm_nn<T>(c, n, l, P, b.ldc, Mc, e, "colour input dgrad")));
         }
     }
     return MSDF_OK;
 }
 
-int sdf_backward(const Ctx& c, const Bufs& b, const float* x, int64_t Mc, const msdf_mlp_grads* gr, float* grad_table) {
+template <class T>
+int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, const msdf_mlp_grads* gr, float* grad_table) {
     const Net& n = c.sn;
     // ---- tangent sweep (adjoint of the reverse sweep) with the a_l^T t_l weight gradients
-    const float* Tin = b.TG0; int64_t ldt = n.d0p;
+    T* Tin = b.TG0; int64_t ldt = b.d0p;
     for (int l = 0; l < n.L - 1; ++l) {
         if (l == n.skip) {
-            k_skip_copy<<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.TG0, n.d0p, const_cast<float*>(Tin), ldt, Mc, n.d0, n.in[l] - n.d0, kInvSqrt2);
+            k_skip_copy<T><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.TG0, b.d0p, Tin, ldt, Mc, n.d0, n.in[l] - n.d0, kInvSqrt2);
             LAUNCHED("tangent skip copy");
         }
-        RUN(wgrad(b.A[l], n.ldh, Tin, ldt, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], c.st));
-        float* Tout = b.T[(l + 1) & 1];
-        EpiTan e{b.H[l + 1], n.ldh, in_scale(n, l + 1), b.A[l], n.ldh, Tout, n.ldh, l + 1 == n.skip ? kInvSqrt2 : 1.0f};
-        RUN((launch<kNT>(Tin, ldt, n.W[l], n.ldw[l], Mc, n.out[l], n.in[l], 1, e, c.st, "sdf tangent layer")));
-        Tin = Tout; ldt = n.ldh;
+        RUN(wgrad<T>(c, b.A[l], b.ldh, Tin, ldt, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+        T* Tout = b.T2[(l + 1) & 1];
+        EpiTan<T> e{};
+        e.Hn = b.H[l + 1]; e.ldh = b.ldh; e.hscale = in_scale(n, l + 1); e.AZ = b.A[l]; e.lda = b.ldh;
+        e.Tout = Tout; e.ldt = b.ldh; e.tscale = l + 1 == n.skip ? kInvSqrt2 : 1.0f;
+        RUN((gemm_nt<T>(c, n, l, Tin, ldt, Mc, 0, n.out[l], e, "sdf tangent layer")));
+        Tin = Tout; ldt = b.ldh;
     }
+    const int L1 = n.L - 1;
+    const int out_last = n.out[L1];
     {
-        const int l = n.L - 1;
-        if (l == n.skip) {
-            k_skip_copy<<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.TG0, n.d0p, const_cast<float*>(Tin), ldt, Mc, n.d0, n.in[l] - n.d0, kInvSqrt2);
+        if (L1 == n.skip) {
+            k_skip_copy<T><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.TG0, b.d0p, Tin, ldt, Mc, n.d0, n.in[L1] - n.d0, kInvSqrt2);
             LAUNCHED("tangent skip copy");
         }
-        RUN(colsum(Tin, ldt, nullptr, 0, Mc, n.in[l], gr->dW[l], c.st));                       // a_{L-1} = e_0
+        RUN(colsum<T>(c, Tin, ldt, nullptr, 0, Mc, n.in[L1], gr->dW[L1]));                          // a_{L-1} = e_0 -> sdf row
         // ---- last layer of the backward sweep: pbar_{L-1} = Dout
-        RUN(colsum(b.H[l], n.ldh, b.Dout, b.ldo, Mc, n.in[l], gr->dW[l], c.st));               // sdf row
-        if (n.out[l] > 1) RUN(wgrad(b.Dout + 1, b.ldo, b.H[l], n.ldh, n.out[l] - 1, n.in[l], Mc, gr->dW[l] + n.ldw[l], n.ldw[l], c.st));
-        RUN(colsum(b.Dout, b.ldo, nullptr, 0, Mc, n.out[l], gr->db[l], c.st));
+        if (kIsBf16<T>) {
+            // Dout columns are [features..., sdf]: one weight-gradient GEMM with the row permutation folded in
+            RUN(wgrad<T>(c, b.Dout, b.ldo, b.H[L1], b.ldh, out_last, n.in[L1], Mc, gr->dW[L1], n.ldw[L1], out_last));
+            if (out_last > 1) RUN(colsum<T>(c, b.Dout, b.ldo, nullptr, 0, Mc, out_last - 1, gr->db[L1] + 1));
+            RUN(colsum<T>(c, b.Dout + (out_last - 1), b.ldo, nullptr, 0, Mc, 1, gr->db[L1]));
+        } else {
+            RUN(colsum<T>(c, b.H[L1], b.ldh, b.Dout, b.ldo, Mc, n.in[L1], gr->dW[L1]));             // sdf row
+            if (out_last > 1)
+                RUN(wgrad<T>(c, b.Dout + 1, b.ldo, b.H[L1], b.ldh, out_last - 1, n.in[L1], Mc, gr->dW[L1] + n.ldw[L1], n.ldw[L1], 0));
+            RUN(colsum<T>(c, b.Dout, b.ldo, nullptr, 0, Mc, out_last, gr->db[L1]));
+        }
     }
-    const float* P = b.Dout; int64_t ldp = b.ldo;
-    for (int l = n.L - 1; l >= 0; --l) {
-        if (l < n.L - 1) {
-            RUN(wgrad(P, ldp, b.H[l], l == 0 ? n.d0p : n.ldh, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], c.st));
-            RUN(colsum(P, ldp, nullptr, 0, Mc, n.out[l], gr->db[l], c.st));
+    const T* P = b.Dout; int64_t ldp = b.ldo;
+    for (int l = L1; l >= 0; --l) {
+        if (l < L1) {
+            RUN(wgrad<T>(c, P, ldp, b.H[l], l == 0 ? b.d0p : b.ldh, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+            RUN(colsum<T>(c, P, ldp, nullptr, 0, Mc, n.out[l], gr->db[l]));
         }
         if (l == 0 && !(c.grid && grad_table)) break;
-        EpiBwd e{};
-        e.Hin = b.H[l]; e.ldh = l == 0 ? n.d0p : n.ldh; e.hscale = in_scale(n, l);
-        e.PZ = l > 0 ? b.A[l - 1] : nullptr; e.ldp = n.ldh;
-        e.bh0 = (c.grid && grad_table) ? b.BH0 : nullptr; e.ldb = n.d0p;
+        EpiBwd<T> e{};
+        e.Hin = b.H[l]; e.ldh = l == 0 ? b.d0p : b.ldh; e.hscale = in_scale(n, l);
+        e.PZ = l > 0 ? b.A[l - 1] : nullptr; e.ldp = b.ldh;
+        e.bh0 = (c.grid && grad_table) ? b.BH0 : nullptr; e.ldb = round_up(n.d0, 4);
         e.dh = l == n.skip ? n.in[l] - n.d0 : n.in[l];
         e.qscale = l == n.skip ? kInvSqrt2 : 1.0f;
         e.layer0 = l == 0; e.bh0_accum = n.skip > 0;
-        RUN((launch<kNN>(P, ldp, n.W[l], n.ldw[l], Mc, n.in[l], n.out[l], 1, e, c.st, "sdf backward layer")));
-        if (l > 0) { P = b.A[l - 1]; ldp = n.ldh; }
+        RUN((gemm_nn<T>(c, n, l, P, ldp, Mc, e, "sdf backward layer")));
+        if (l > 0) { P = b.A[l - 1]; ldp = b.ldh; }
     }
     if (c.grid && grad_table) {
+        const int64_t ldg = round_up(n.d0, 4);
         RUN(msdf_hash_scatter_rows(x, c.enc->offsets, Mc, c.enc->level_dim, c.enc->n_levels, c.enc->log2_per_level_scale,
-                                   (uint32_t)c.enc->base_res, c.enc->divide_factor, b.BH0 + c.pe_w, n.d0p, b.G0 + c.pe_w, n.d0p,
+                                   (uint32_t)c.enc->base_res, c.enc->divide_factor, b.BH0 + c.pe_w, ldg, b.G0 + c.pe_w, ldg,
                                    b.dn, c.hash_chain, grad_table, c.st));
     }
     return MSDF_OK;
 }
 
 int make_ctx(Ctx& c, const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
-             const msdf_color_desc* cd, float clamp_radius, float sphere_scale, void* stream, const char* who) {
+             const msdf_color_desc* cd, float clamp_radius, float sphere_scale, void* stream, unsigned flags, const char* who) {
     MSDF_CHECK_ARG(enc != nullptr, "%s: null encoding descriptor", who);
     RUN(make_net(sdf_net, c.sn, who));
     c.enc = enc;
@@ -795,8 +1078,116 @@ int make_ctx(Ctx& c, const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc
         MSDF_CHECK_ARG(cd->feat_dim == c.sn.out[c.sn.L - 1] - 1, "%s: feat_dim mismatch", who);
         MSDF_CHECK_ARG(c.cd->multires_view <= 16, "%s: multires_view too large", who);
     }
+    if (flags & MSDF_FLAG_TENSOR_BF16) {
+        RUN(check_tc_net(c.sn, who));
+        if (c.has_color) RUN(check_tc_net(c.cn, who));
+    }
     c.clamp_radius = clamp_radius; c.sphere_scale = sphere_scale;
     c.st = (cudaStream_t)stream;
+    return MSDF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// forward / backward drivers, generic over T
+// ----------------------------------------------------------------------------------------------------------
+template <class T>
+int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int n_samples, const float* code, int mode,
+                  void* workspace, size_t workspace_bytes, float* sdf, float* grad, float* feat, int64_t ld_feat, float* rgb,
+                  const char* who) {
+    int64_t chunk = pick_chunk<T>(c, M, mode, workspace_bytes);
+    MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
+                   carve<T>(c, 128, mode, nullptr, nullptr, nullptr, nullptr));
+    if (c.has_color && chunk < M) {   // keep chunks ray aligned
+        chunk = chunk / n_samples * n_samples;
+        MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
+    }
+    Bufs<T> b{};
+    carve<T>(c, (chunk + 127) / 128 * 128, mode, workspace, &b, &c.sn, &c.cn);
+    if (kIsBf16<T>) {
+        RUN(prep_weights(c, c.sn, 1));
+        if (c.has_color) RUN(prep_weights(c, c.cn, 0));
+    }
+    const bool with_grad = mode == MSDF_MODE_FORWARD && (grad != nullptr);
+    MSDF_CHECK_ARG(!(kIsBf16<T> && feat != nullptr), "%s: the raw feature output is only available in fp32 mode", who);
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int64_t Mc = (M - m0 < chunk) ? M - m0 : chunk;
+        const float* xc = x + 3 * m0;
+        RUN(encode_chunk<T>(c, b, xc, Mc, with_grad));
+        T* featc = nullptr; int64_t ldf_ = 0;
+        if (c.has_color) { featc = b.X + c.cg.fc; ldf_ = b.ldx; }
+        else if (feat != nullptr) { featc = reinterpret_cast<T*>(feat + m0 * ld_feat); ldf_ = ld_feat; }
+        RUN(forward_sweep<T>(c, b, Mc, featc, ldf_));
+        if (with_grad) RUN(reverse_sweep<T>(c, b, Mc));
+        RUN(decode_chunk<T>(c, b, xc, Mc, with_grad, sdf ? sdf + m0 : nullptr, with_grad ? grad + 3 * m0 : nullptr, nullptr));
+        if (c.has_color) {
+            const int64_t ray0 = m0 / n_samples;
+            RUN(color_forward<T>(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
+                                 code ? code + (c.cd->code_per_ray ? ray0 * c.cd->code_dim : 0) : nullptr, grad + 3 * m0,
+                                 rgb + (int64_t)c.cn.out[c.cn.L - 1] * m0));
+        }
+    }
+    return MSDF_OK;
+}
+
+template <class T>
+int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int n_samples, const float* code, void* workspace,
+                   size_t workspace_bytes, const float* d_sdf, const float* d_grad, const float* d_feat, int64_t ld_dfeat,
+                   const float* rgb, const float* d_rgb, const msdf_mlp_grads* sdf_grads, const msdf_mlp_grads* color_grads,
+                   float* grad_table, float* d_code, const char* who) {
+    int64_t chunk = pick_chunk<T>(c, M, MSDF_MODE_BACKWARD, workspace_bytes);
+    MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
+                   carve<T>(c, 128, MSDF_MODE_BACKWARD, nullptr, nullptr, nullptr, nullptr));
+    if (c.has_color && chunk < M) {   // keep chunks ray aligned
+        chunk = chunk / n_samples * n_samples;
+        MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
+    }
+    Bufs<T> b{};
+    carve<T>(c, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, workspace, &b, &c.sn, &c.cn);
+    if (kIsBf16<T>) {
+        RUN(prep_weights(c, c.sn, 1));
+        if (c.has_color) RUN(prep_weights(c, c.cn, 0));
+    }
+    const int out_last = c.sn.out[c.sn.L - 1];
+    const int feat_w = out_last - 1;
+    const int sdf_col = kIsBf16<T> ? feat_w : 0, feat_col0 = kIsBf16<T> ? 0 : 1;
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int64_t Mc = (M - m0 < chunk) ? M - m0 : chunk;
+        const float* xc = x + 3 * m0;
+        // ---- recompute the chunk
+        RUN(encode_chunk<T>(c, b, xc, Mc, true));
+        RUN(forward_sweep<T>(c, b, Mc, c.has_color ? b.X + c.cg.fc : nullptr, c.has_color ? b.ldx : 0));
+        RUN(reverse_sweep<T>(c, b, Mc));
+        RUN(decode_chunk<T>(c, b, xc, Mc, true, b.sdfc, b.gradc, b.mask));
+        if (c.has_color) {
+            const int64_t ray0 = m0 / n_samples;
+            const int no = c.cn.out[c.cn.L - 1];
+            const msdf_color_desc* cd = c.cd;
+            RUN(color_forward<T>(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
+                                 code ? code + (cd->code_per_ray ? ray0 * cd->code_dim : 0) : nullptr, b.gradc, nullptr));
+            RUN(color_backward<T>(c, b, Mc, rgb + (int64_t)no * m0, d_rgb + (int64_t)no * m0, color_grads));
+            if (cd->code_dim > 0 && d_code) {
+                if (cd->code_per_ray) {
+                    const int64_t nr = Mc / n_samples;
+                    k_code_grad<<<nblk(nr * cd->code_dim), 256, 0, c.st>>>(b.dcode, nr, n_samples, cd->code_dim, d_code + ray0 * cd->code_dim);
+                    LAUNCHED("per-ray code gradient");
+                } else {
+                    RUN(colsum<float>(c, b.dcode, cd->code_dim, nullptr, 0, Mc, cd->code_dim, d_code));
+                }
+            }
+        }
+        // ---- adjoints of (sdf, feat, grad) -> tangent of the encoded input
+        {
+            const int t_cols = (int)b.d0p, out_cols = (int)b.ldo;
+            const int cols = t_cols > out_cols ? t_cols : out_cols;
+            k_backward_prologue<T><<<nblk(Mc * cols), 256, 0, c.st>>>(
+                xc, Mc, c.pe_w, c.enc->grid_feat_dim, c.enc->n_levels, c.enc->level_dim, c.grid ? b.dydx : nullptr, c.hash_chain,
+                b.mask, d_sdf ? d_sdf + m0 : nullptr, d_grad ? d_grad + 3 * m0 : nullptr, c.has_color ? b.dn_color : nullptr,
+                d_feat ? d_feat + m0 * ld_dfeat : nullptr, ld_dfeat, feat_w, c.has_color ? 1 : 0, sdf_col, feat_col0, b.Dout, b.ldo,
+                out_cols, b.dn, b.TG0, b.d0p, t_cols);
+            LAUNCHED("backward prologue");
+        }
+        RUN(sdf_backward<T>(c, b, xc, Mc, sdf_grads, grad_table));
+    }
     return MSDF_OK;
 }
 
@@ -808,17 +1199,18 @@ int make_ctx(Ctx& c, const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc
 extern "C" size_t msdf_field_workspace_bytes(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc,
                                              const msdf_mlp_desc* color_net, const msdf_color_desc* cd, int64_t chunk_points,
                                              int mode, unsigned flags) {
-    (void)flags;
     Ctx c{};
     msdf_mlp_desc tmp_s = *sdf_net;
     static const float dummy = 0.f;
     for (int l = 0; l < tmp_s.n_layers && l < MSDF_MAX_LAYERS; ++l) { if (!tmp_s.W[l]) tmp_s.W[l] = &dummy; if (!tmp_s.b[l]) tmp_s.b[l] = &dummy; }
     msdf_mlp_desc tmp_c{};
     if (color_net) { tmp_c = *color_net; for (int l = 0; l < tmp_c.n_layers && l < MSDF_MAX_LAYERS; ++l) { if (!tmp_c.W[l]) tmp_c.W[l] = &dummy; if (!tmp_c.b[l]) tmp_c.b[l] = &dummy; } }
-    if (make_ctx(c, &tmp_s, enc, color_net ? &tmp_c : nullptr, cd, 0.f, 1.f, nullptr, "msdf_field_workspace_bytes")) return 0;
+    if (mode == MSDF_MODE_SDF_ONLY) color_net = nullptr;
+    if (make_ctx(c, &tmp_s, enc, color_net ? &tmp_c : nullptr, cd, 0.f, 1.f, nullptr, flags, "msdf_field_workspace_bytes")) return 0;
     int64_t mc = (chunk_points + 127) / 128 * 128;
     if (mc < 128) mc = 128;
-    return carve(c.sn, enc, c.has_color ? &c.cn : nullptr, cd, mc, mode, nullptr, nullptr);
+    if (flags & MSDF_FLAG_TENSOR_BF16) return carve<bf16>(c, mc, mode, nullptr, nullptr, nullptr, nullptr);
+    return carve<float>(c, mc, mode, nullptr, nullptr, nullptr, nullptr);
 }
 
 extern "C" int msdf_field_forward(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
@@ -828,49 +1220,21 @@ extern "C" int msdf_field_forward(const msdf_mlp_desc* sdf_net, const msdf_encod
                                   float* feat, int64_t ld_feat, float* rgb, void* stream) {
     const char* who = "msdf_field_forward";
     MSDF_CHECK_ARG(mode == MSDF_MODE_SDF_ONLY || mode == MSDF_MODE_FORWARD, "%s: bad mode %d", who, mode);
-    MSDF_CHECK_ARG((flags & MSDF_FLAG_TENSOR_BF16) == 0, "%s: tensor-core path not built into this entry point yet", who);
     if (mode == MSDF_MODE_SDF_ONLY) color_net = nullptr;
+    if (feat != nullptr) flags &= ~MSDF_FLAG_TENSOR_BF16;   // raw feature output: fp32 engine
     Ctx c{};
-    RUN(make_ctx(c, sdf_net, enc, color_net, cd, clamp_radius, sphere_scale, stream, who));
+    RUN(make_ctx(c, sdf_net, enc, color_net, cd, clamp_radius, sphere_scale, stream, flags, who));
     if (M == 0) return MSDF_OK;
     MSDF_CHECK_ARG(x && workspace, "%s: null x / workspace", who);
     MSDF_CHECK_ARG(mode == MSDF_MODE_SDF_ONLY || grad != nullptr || !c.has_color, "%s: grad output required with a colour net", who);
     if (c.has_color) {
         MSDF_CHECK_ARG(view_dirs && rgb && n_samples > 0 && n_rays * (int64_t)n_samples == M, "%s: colour net needs view_dirs, rgb and M == n_rays*n_samples", who);
         MSDF_CHECK_ARG(cd->code_dim == 0 || code, "%s: per-image code missing", who);
+        MSDF_CHECK_ARG(feat == nullptr, "%s: feat output and colour net are mutually exclusive", who);
     }
-    const Net* cn = c.has_color ? &c.cn : nullptr;
-    int64_t chunk = pick_chunk(c.sn, enc, cn, cd, M, mode, workspace_bytes);
-    MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
-                   carve(c.sn, enc, cn, cd, 128, mode, nullptr, nullptr));
-    if (c.has_color && chunk < M) {   // keep chunks ray aligned
-        chunk = chunk / n_samples * n_samples;
-        MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
-    }
-    Bufs b{};
-    carve(c.sn, enc, cn, cd, (chunk + 127) / 128 * 128, mode, workspace, &b);
-    const bool with_grad = mode == MSDF_MODE_FORWARD && (grad != nullptr);
-    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
-        const int64_t Mc = (M - m0 < chunk) ? M - m0 : chunk;
-        const float* xc = x + 3 * m0;
-        RUN(encode_chunk(c, b, xc, Mc, with_grad));
-        float* featc = feat ? feat + m0 * ld_feat : nullptr; int64_t ldf = ld_feat;
-        if (c.has_color) {
-            MSDF_CHECK_ARG(feat == nullptr, "%s: feat output and colour net are mutually exclusive", who);
-            featc = b.X + c.cg.fc; ldf = c.cg.ldx;
-        }
-        RUN(forward_sweep(c, b, Mc, featc, ldf));
-        if (with_grad) RUN(reverse_sweep(c, b, Mc));
-        RUN(decode_chunk(c, b, xc, Mc, with_grad, sdf ? sdf + m0 : nullptr, with_grad ? grad + 3 * m0 : nullptr, nullptr));
-        if (c.has_color) {
-            // rays of this chunk: point m0+i belongs to ray (m0+i)/n_samples -> chunk must start on a ray boundary
-            const int64_t ray0 = m0 / n_samples;
-            MSDF_CHECK_ARG(m0 % n_samples == 0, "%s: internal: chunk not ray aligned", who);
-            RUN(color_forward(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
-                              code ? code + (cd->code_per_ray ? ray0 * cd->code_dim : 0) : nullptr, grad + 3 * m0, rgb + (int64_t)c.cn.out[c.cn.L - 1] * m0));
-        }
-    }
-    return MSDF_OK;
+    if (flags & MSDF_FLAG_TENSOR_BF16)
+        return field_forward<bf16>(c, x, M, view_dirs, n_samples, code, mode, workspace, workspace_bytes, sdf, grad, feat, ld_feat, rgb, who);
+    return field_forward<float>(c, x, M, view_dirs, n_samples, code, mode, workspace, workspace_bytes, sdf, grad, feat, ld_feat, rgb, who);
 }
 
 extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
@@ -881,10 +1245,9 @@ extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_enco
                                    const msdf_mlp_grads* sdf_grads, const msdf_mlp_grads* color_grads, float* grad_table,
                                    float* d_code, void* stream) {
     const char* who = "msdf_field_backward";
-    MSDF_CHECK_ARG((flags & MSDF_FLAG_TENSOR_BF16) == 0, "%s: tensor-core path not built into this entry point yet", who);
     if (d_rgb == nullptr) color_net = nullptr;
     Ctx c{};
-    RUN(make_ctx(c, sdf_net, enc, color_net, cd, clamp_radius, sphere_scale, stream, who));
+    RUN(make_ctx(c, sdf_net, enc, color_net, cd, clamp_radius, sphere_scale, stream, flags, who));
     if (M == 0) return MSDF_OK;
     MSDF_CHECK_ARG(x && workspace && sdf_grads, "%s: null x / workspace / sdf_grads", who);
     for (int l = 0; l < c.sn.L; ++l) MSDF_CHECK_ARG(sdf_grads->dW[l] && sdf_grads->db[l], "%s: sdf grad buffer %d missing", who, l);
@@ -893,54 +1256,11 @@ extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_enco
         for (int l = 0; l < c.cn.L; ++l) MSDF_CHECK_ARG(color_grads->dW[l] && color_grads->db[l], "%s: colour grad buffer %d missing", who, l);
         MSDF_CHECK_ARG(cd->code_dim == 0 || code, "%s: per-image code missing", who);
     }
-    const Net* cn = c.has_color ? &c.cn : nullptr;
-    int64_t chunk = pick_chunk(c.sn, enc, cn, cd, M, MSDF_MODE_BACKWARD, workspace_bytes);
-    MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
-                   carve(c.sn, enc, cn, cd, 128, MSDF_MODE_BACKWARD, nullptr, nullptr));
-    if (c.has_color && chunk < M) {   // keep chunks ray aligned
-        chunk = chunk / n_samples * n_samples;
-        MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
-    }
-    Bufs b{};
-    carve(c.sn, enc, cn, cd, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, workspace, &b);
-    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
-        const int64_t Mc = (M - m0 < chunk) ? M - m0 : chunk;
-        const float* xc = x + 3 * m0;
-        // ---- recompute the chunk
-        RUN(encode_chunk(c, b, xc, Mc, true));
-        RUN(forward_sweep(c, b, Mc, c.has_color ? b.X + c.cg.fc : nullptr, c.has_color ? c.cg.ldx : 0));
-        RUN(reverse_sweep(c, b, Mc));
-        RUN(decode_chunk(c, b, xc, Mc, true, b.sdfc, b.gradc, b.mask));
-        if (c.has_color) {
-            const int64_t ray0 = m0 / n_samples;
-            const int no = c.cn.out[c.cn.L - 1];
-            RUN(color_forward(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
-                              code ? code + (cd->code_per_ray ? ray0 * cd->code_dim : 0) : nullptr, b.gradc, nullptr));
-            RUN(color_backward(c, b, Mc, rgb + (int64_t)no * m0, d_rgb + (int64_t)no * m0, color_grads));
-            if (cd->code_dim > 0 && d_code) {
-                if (cd->code_per_ray) {
-                    const int64_t nr = Mc / n_samples;
-                    k_code_grad<<<nblk(nr * cd->code_dim), 256, 0, c.st>>>(b.dcode, nr, n_samples, cd->code_dim, d_code + ray0 * cd->code_dim);
-                    LAUNCHED("per-ray code gradient");
-                } else {
-                    RUN(colsum(b.dcode, cd->code_dim, nullptr, 0, Mc, cd->code_dim, d_code, c.st));
-                }
-            }
-        }
-        // ---- adjoints of (sdf, feat, grad) -> tangent of the encoded input
-        {
-            const int feat_w = c.sn.out[c.sn.L - 1] - 1;
-            const int d0 = c.sn.d0;
-            const int cols = d0 > feat_w + 1 ? d0 : feat_w + 1;
-            k_backward_prologue<<<nblk(Mc * cols), 256, 0, c.st>>>(
-                xc, Mc, c.pe_w, c.enc->grid_feat_dim, c.enc->n_levels, c.enc->level_dim, c.grid ? b.dydx : nullptr, c.hash_chain,
-                b.mask, d_sdf ? d_sdf + m0 : nullptr, d_grad ? d_grad + 3 * m0 : nullptr, c.has_color ? b.dn_color : nullptr,
-                d_feat ? d_feat + m0 * ld_dfeat : nullptr, ld_dfeat, feat_w, c.has_color ? 1 : 0, b.Dout, b.ldo, b.dn, b.TG0, c.sn.d0p);
-            LAUNCHED("backward prologue");
-        }
-        RUN(sdf_backward(c, b, xc, Mc, sdf_grads, grad_table));
-    }
-    return MSDF_OK;
+    if (flags & MSDF_FLAG_TENSOR_BF16)
+        return field_backward<bf16>(c, x, M, view_dirs, n_samples, code, workspace, workspace_bytes, d_sdf, d_grad, d_feat, ld_dfeat,
+                                    rgb, d_rgb, sdf_grads, color_grads, grad_table, d_code, who);
+    return field_backward<float>(c, x, M, view_dirs, n_samples, code, workspace, workspace_bytes, d_sdf, d_grad, d_feat, ld_dfeat,
+                                 rgb, d_rgb, sdf_grads, color_grads, grad_table, d_code, who);
 }
 
 extern "C" int msdf_ray_points(const float* ray_o, const float* ray_d, const float* z, int64_t n_rays, int n, float* points,

@@ -24,7 +24,7 @@ from .embedder import get_embedder
 from .ray_sampler import ErrorBoundSampler
 
 _GB = 1 << 30
-WORKSPACE_CAP_BYTES = 3 * _GB     # per-call scratch; the library chunks the points to fit
+WORKSPACE_CAP_BYTES = 6 * _GB     # per-call scratch; the library chunks the points to fit
 
 
 def _round4(n):
@@ -128,7 +128,8 @@ class _FieldSpec:
 
 
 def _workspace_for(sdf_d, enc_d, col_d, cd_d, M, mode, flags, device):
-    chunk = min(max(int(M), 128), 65536 if mode != _lib.MODE_SDF_ONLY else 262144)
+    cap = 524288 if mode == _lib.MODE_SDF_ONLY else (262144 if flags & _lib.FLAG_TENSOR_BF16 else 65536)
+    chunk = min(max(int(M), 128), cap)
     need = _lib.lib().msdf_field_workspace_bytes(sdf_d, enc_d, col_d, cd_d, chunk, mode, flags)
     if need == 0:
         raise RuntimeError("monosdf_b200: msdf_field_workspace_bytes failed: " + _lib.lib().msdf_last_error().decode())

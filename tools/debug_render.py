@@ -12,6 +12,8 @@ DEV = "cuda"
 case = sys.argv[1] if len(sys.argv) > 1 else "mlp_small"
 fx = torch.load(os.path.join("tests/golden", case + ".pt"), map_location="cpu", weights_only=False)
 model = build_model(fx, DEV)
+if len(sys.argv) > 2:
+    model.set_precision(sys.argv[2])
 cfg = port.cfg_from_conf(fx["conf"])
 n_rays, S = 96, 40
 rays = port.synthetic_rays(n_rays, seed=9)
