@@ -312,10 +312,10 @@ int msdf_hash_scatter_rows(const float* x, const int* offsets, int64_t B, int C,
 extern "C" int msdf_hash_encode_forward(const float* inputs, const float* embeddings, const int32_t* offsets, float* outputs,
                                         uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
                                         int calc_grad_inputs, float* dy_dx, void* stream) {
+    if (B == 0) return MSDF_OK;
     MSDF_CHECK_ARG(inputs && embeddings && offsets && outputs, "msdf_hash_encode_forward: null pointer");
     MSDF_CHECK_ARG(D == 3, "msdf_hash_encode_forward: only D=3 is built (got D=%u)", D);
     MSDF_CHECK_ARG(!calc_grad_inputs || dy_dx, "msdf_hash_encode_forward: dy_dx required when calc_grad_inputs");
-    if (B == 0) return MSDF_OK;
     cudaStream_t st = (cudaStream_t)stream;
     float* dd = calc_grad_inputs ? dy_dx : nullptr;
     switch (C) {

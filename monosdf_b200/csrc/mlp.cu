@@ -125,6 +125,7 @@ struct Net {
     // bf16 copies for the tensor-core path (prepared per call): Wk = W (K-major over the inputs), Wt = W^T
     bf16* Wk[MSDF_MAX_LAYERS]; bf16* Wt[MSDF_MAX_LAYERS];
     int perm_last;     // 1: rows of the last layer are ordered [features..., sdf] in Wk/Wt (bf16 SDF net)
+    int rot0;          // bf16 copies of layer 0: input column k' holds W[:, (k' + rot0) % in] (rotated colour input)
 };
 
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -134,7 +135,7 @@ int make_net(const msdf_mlp_desc* d, Net& n, const char* who) {
     MSDF_CHECK_ARG(d != nullptr, "%s: null network descriptor", who);
     MSDF_CHECK_ARG(d->n_layers >= 2 && d->n_layers <= MSDF_MAX_LAYERS, "%s: n_layers=%d not in [2,%d]", who, d->n_layers,
                    MSDF_MAX_LAYERS);
-    n.L = d->n_layers; n.d0 = d->d0; n.skip = d->skip_layer; n.perm_last = 0;
+    n.L = d->n_layers; n.d0 = d->d0; n.skip = d->skip_layer; n.perm_last = 0; n.rot0 = 0;
     MSDF_CHECK_ARG(n.skip < n.L && n.skip != 0, "%s: skip_layer=%d invalid", who, n.skip);
     int w = 0;
     for (int l = 0; l < n.L; ++l) {
@@ -405,11 +406,11 @@ struct EpiBase {
     __device__ __forceinline__ void operator()(int64_t m, int n, const float v[4], int nv) const {
         static_cast<const Derived*>(this)->template run<4>(m, n, v, nv);
     }
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[8]) const {
-        const int nv = N - n;
-        if (nv > 0) static_cast<const Derived*>(this)->template run<8>(m, n, v, nv < 8 ? nv : 8);
-    }
+    // tcgen05 engine: number of valid columns of the 32-column chunk starting at n0 (<= 0: nothing to do)
+    __device__ __forceinline__ int chunk_cols(int n0) const { const int nv = N - n0; return nv < 32 ? nv : 32; }
 };
+
+using msdf_tc::WarpIO;
 
 template <class T>
 struct EpiFwdAct : EpiBase<EpiFwdAct<T>> {   // out[m,n] = softplus100(acc + b[n]) * oscale
@@ -419,6 +420,13 @@ struct EpiFwdAct : EpiBase<EpiFwdAct<T>> {   // out[m,n] = softplus100(acc + b[n
 #pragma unroll
         for (int j = 0; j < W; ++j) o[j] = j < nv ? softplus100<kIsBf16<T>>(v[j] + __ldg(bias + n + j)) * oscale : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
+    }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < nv ? softplus100<true>(v[j] + __ldg(bias + n0 + j)) * oscale : 0.f;
+        io.store(out, ldo, n0, v, nv);
     }
 };
 template <class T>
@@ -430,6 +438,13 @@ struct EpiBias : EpiBase<EpiBias<T>> {       // out[m,n] = acc + b[n]
         for (int j = 0; j < W; ++j) o[j] = j < nv ? v[j] + __ldg(bias + n + j) : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
     }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < nv ? v[j] + __ldg(bias + n0 + j) : 0.f;
+        io.store(out, ldo, n0, v, nv);
+    }
 };
 template <class T>
 struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
@@ -440,11 +455,19 @@ struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
         for (int j = 0; j < W; ++j) o[j] = j < nv ? fmaxf(v[j] + __ldg(bias + n + j), 0.f) : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
     }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = j < nv ? fmaxf(v[j] + __ldg(bias + n0 + j), 0.f) : 0.f;
+        io.store(out, ldo, n0, v, nv);
+    }
 };
 // C[row(m), n] += acc  (split-K weight gradients).  With perm_rows > 0 the GEMM's row index i addresses the
 // permuted last layer [features..., sdf]: i < perm_rows - 1 -> row i + 1, i == perm_rows - 1 -> row 0.
 struct EpiAtomic : EpiBase<EpiAtomic> {
     float* C; int64_t ldc; int Mrows; int perm_rows;
+    int col_rot;                                   // GEMM column c addresses column (c + col_rot) % N (rotated colour input)
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         if (m >= Mrows) return;
         const int64_t r = perm_rows > 0 ? (m == perm_rows - 1 ? 0 : m + 1) : m;
@@ -452,6 +475,18 @@ struct EpiAtomic : EpiBase<EpiAtomic> {
 #pragma unroll
         for (int j = 0; j < W; ++j)
             if (j < nv) atomicAdd(o + j, v[j]);
+    }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+        const EpiAtomic e = *this;
+        io.atomic_add(v, (int64_t)Mrows, [=](int64_t m, int c) -> float* {
+            if (c >= nv) return nullptr;
+            const int64_t r = e.perm_rows > 0 ? (m == e.perm_rows - 1 ? 0 : m + 1) : m;
+            int col = n0 + c + e.col_rot;
+            if (col >= e.N) col -= e.N;
+            return e.C + r * e.ldc + col;
+        });
     }
 };
 // reverse sweep, layer l: acc = (a_l W_l)[m,n], n over the layer's inputs
@@ -481,6 +516,30 @@ struct EpiRev : EpiBase<EpiRev<T>> {
             else stf(Aout + m * lda + c, r * sig_from_h<kIsBf16<T>>(ldf(Hin + m * ldh + c) * hscale));
         }
     }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+        if (layer0) {                              // everything is d sdf / d h0
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= qscale;
+            io.store_f32(g0, ldg, n0, v, 0, nv, g0_accum != 0);
+            return;
+        }
+        const int nh = dh - n0 < nv ? dh - n0 : nv;   // hidden columns of this chunk
+        if (nh < nv) {                             // h0 half of the skip concat
+            float r[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = v[j] * qscale;
+            io.store_f32(g0, ldg, n0 - dh, r, nh > 0 ? nh : 0, nv, false);
+        }
+        if (nh > 0) {
+            float h[32];
+            io.load(Hin, ldh, n0, h);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(h[j] * hscale);
+            io.store(Aout, lda, n0, v, nh);
+        }
+    }
 };
 // tangent sweep, layer l: acc = (t_l W_l^T)[m,n], n over the layer's outputs
 template <class T>
@@ -501,6 +560,22 @@ struct EpiTan : EpiBase<EpiTan<T>> {
         }
         store_row<W>(Tout + m * ldt + n, t, nv);
         store_row<W>(AZ + m * lda + n, z, nv);
+    }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+        float h[32], z[32];
+        io.load(Hn, ldh, n0, h);
+        io.load(AZ, lda, n0, z);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            float s, d;
+            sig_dsig_from_h<true>(h[j] * hscale, s, d);
+            z[j] = v[j] * z[j] * d;
+            v[j] = v[j] * s * tscale;
+        }
+        io.store(Tout, ldt, n0, v, nv);
+        io.store(AZ, lda, n0, z, nv);
     }
 };
 // backward sweep, layer l: acc = (pbar_l W_l)[m,n], n over the layer's inputs
@@ -530,6 +605,32 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
             else { T* p = PZ + m * ldp + c; stf(p, r * sig_from_h<kIsBf16<T>>(ldf(Hin + m * ldh + c) * hscale) + ldf(p)); }
         }
     }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+        if (layer0) {
+            if (bh0 == nullptr) return;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= qscale;
+            io.store_f32(bh0, ldb, n0, v, 0, nv, bh0_accum != 0);
+            return;
+        }
+        const int nh = dh - n0 < nv ? dh - n0 : nv;
+        if (nh < nv && bh0 != nullptr) {
+            float r[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = v[j] * qscale;
+            io.store_f32(bh0, ldb, n0 - dh, r, nh > 0 ? nh : 0, nv, false);
+        }
+        if (nh > 0) {
+            float h[32], z[32];
+            io.load(Hin, ldh, n0, h);
+            io.load(PZ, ldp, n0, z);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(h[j] * hscale) + z[j];
+            io.store(PZ, ldp, n0, v, nh);
+        }
+    }
 };
 template <class T>
 struct EpiBwdRelu : EpiBase<EpiBwdRelu<T>> {  // colour net dgrad: out[m,n] = acc * [Hin[m,n] > 0]
@@ -541,6 +642,15 @@ struct EpiBwdRelu : EpiBase<EpiBwdRelu<T>> {  // colour net dgrad: out[m,n] = ac
         for (int j = 0; j < W; ++j) o[j] = h[j] > 0.f ? v[j] : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
     }
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+        float h[32];
+        io.load(Hin, ldh, n0, h);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
+        io.store(out, ldo, n0, v, nv);
+    }
 };
 // colour net layer-0 dgrad: route d(input) columns to the SDF net's adjoints
 template <class T>
@@ -548,6 +658,7 @@ struct EpiColorIn : EpiBase<EpiColorIn<T>> {
     int n_off;                                     // column offset of this launch (the tcgen05 engine splits N > 256)
     int nc, fc, F, cc, cd;                         // column of the normal (-1 = none), of feat, of the code
     float* dn; T* Dout; int64_t ldo; int feat_col0; float* dcode; int64_t ldc;
+    int rot, in0;                                  // GEMM column c is input column (c + rot) % in0 (bf16 mode: rot = fc)
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         const int c0 = n + n_off;
 #pragma unroll
@@ -559,8 +670,25 @@ struct EpiColorIn : EpiBase<EpiColorIn<T>> {
             else if (cd > 0 && c >= cc && c < cc + cd) dcode[m * ldc + (c - cc)] = v[j];
         }
     }
+    // bf16 mode: the input is stored rotated so that feat starts at column 0 -> whole chunks of feat columns
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+        const int g0c = n0 + n_off;                // first rotated column of the chunk
+        if (g0c + 32 <= F) { io.store(Dout, ldo, feat_col0 + g0c, v, 32); return; }
+        if (g0c < F) io.store(Dout, ldo, feat_col0 + g0c, v, F - g0c);
+        if (cd > 0) {                              // code columns follow feat in the original order
+            const int jlo = cc - rot - g0c;        // rotated column of code[0] is cc - rot
+            io.store_f32(dcode, ldc, -jlo, v, jlo > 0 ? jlo : 0, jlo + cd < nv ? jlo + cd : nv, false);
+        }
+        if (nc >= 0 && io.valid()) {
+            const int jn = in0 - rot + nc - g0c;   // nc < rot: the normal sits after the wrap-around
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j >= jn && j < jn + 3 && j < nv) dn[3 * io.row() + (j - jn)] = v[j];
+        }
+    }
 };
-
 // reverse-sweep start: a_{L-1} = e_0, so (a W_{L-1})[m,n] = W_{L-1}[0,n] for every point
 template <class T>
 __global__ void k_rev_init(const float* __restrict__ w_row, int64_t M, int N, EpiRev<T> epi) {
@@ -579,7 +707,7 @@ __global__ void k_rev_init(const float* __restrict__ w_row, int64_t M, int N, Ep
 template <class T>
 __global__ void k_color_input(const float* __restrict__ x, const float* __restrict__ view, const float* __restrict__ normal,
                               const float* __restrict__ code, int64_t M, int n_samples, int mode_idr, int pe_w, int F, int cd,
-                              int code_per_ray, T* __restrict__ X, int64_t ldx, int pad_cols) {
+                              int code_per_ray, T* __restrict__ X, int64_t ldx, int pad_cols, int rot) {
     const int pre = (mode_idr ? 3 : 0) + pe_w + (mode_idr ? 3 : 0);
     const int cols = pre + cd + pad_cols;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -601,6 +729,8 @@ __global__ void k_color_input(const float* __restrict__ x, const float* __restri
             else v = normal[3 * m + (j - pe_w)];
         }
     }
+    const int in0 = pre + F + cd;
+    if (rot > 0 && col < in0) { col -= rot; if (col < 0) col += in0; }
     stf(X + m * ldx + col, v);
 }
 
@@ -625,20 +755,20 @@ __global__ void k_code_grad(const float* __restrict__ dcode, int64_t n_rays, int
 
 // bf16 weight preparation for the tensor-core path.  Wk[r, k] = W[row(r), k] (zero padded to [rows_p, in_p]),
 // Wt[k, r] = W[row(r), k] (zero padded to [in_p16, rows_p64]); row(r) applies the [features..., sdf] permutation.
-__global__ void k_prep_weights(const float* __restrict__ W, int64_t ldw, int out, int in, int perm, bf16* __restrict__ Wk,
+__global__ void k_prep_weights(const float* __restrict__ W, int64_t ldw, int out, int in, int perm, int rot, bf16* __restrict__ Wk,
                                int wk_rows, int wk_ld, bf16* __restrict__ Wt, int wt_rows, int wt_ld) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nk = (int64_t)wk_rows * wk_ld, nt = (int64_t)wt_rows * wt_ld;
     if (i < nk) {
         const int r = (int)(i / wk_ld), k = (int)(i - (int64_t)r * wk_ld);
         float v = 0.f;
-        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + k]; }
+        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + (k + rot) % in]; }
         Wk[i] = __float2bfloat16(v);
     } else if (i < nk + nt) {
         const int64_t t = i - nk;
         const int k = (int)(t / wt_ld), r = (int)(t - (int64_t)k * wt_ld);
         float v = 0.f;
-        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + k]; }
+        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + (k + rot) % in]; }
         Wt[t] = __float2bfloat16(v);
     }
 }
@@ -797,9 +927,9 @@ int gemm_nn(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t 
 // dW[rows, cols] += X^T Y, X [Mc, rows], Y [Mc, cols]
 template <class T>
 int wgrad(const Ctx& c, const T* X, int64_t ldx, const T* Y, int64_t ldy, int rows, int cols, int64_t Mc, float* dW, int64_t ldw,
-          int perm_rows) {
+          int perm_rows, int col_rot = 0) {
     EpiAtomic e{};
-    e.N = cols; e.C = dW; e.ldc = ldw; e.Mrows = rows; e.perm_rows = perm_rows;
+    e.N = cols; e.C = dW; e.ldc = ldw; e.Mrows = rows; e.perm_rows = perm_rows; e.col_rot = col_rot;
     if constexpr (kIsBf16<T>) {
         return msdf_tc::launch_wgrad(X, ldx, round_up(rows, 64), Y, ldy, round_up(cols, 64), Mc, e, c.st, "weight gradient");
     } else {
@@ -825,7 +955,7 @@ int prep_weights(const Ctx& c, Net& n, int perm_last) {
         const int wk_rows = round_up(n.out[l], 16), wk_ld = round_up(n.in[l], 64);
         const int wt_rows = round_up(n.in[l], 16), wt_ld = round_up(n.out[l], 64);
         const int64_t total = (int64_t)wk_rows * wk_ld + (int64_t)wt_rows * wt_ld;
-        k_prep_weights<<<nblk(total), 256, 0, c.st>>>(n.W[l], n.ldw[l], n.out[l], n.in[l], perm, n.Wk[l], wk_rows, wk_ld, n.Wt[l],
+        k_prep_weights<<<nblk(total), 256, 0, c.st>>>(n.W[l], n.ldw[l], n.out[l], n.in[l], perm, l == 0 ? n.rot0 : 0, n.Wk[l], wk_rows, wk_ld, n.Wt[l],
                                                      wt_rows, wt_ld);
         LAUNCHED("weight prep");
     }
@@ -935,7 +1065,7 @@ int color_forward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, co
     const int cols = g.in0 - c.cd->feat_dim + pad;
     // chunks start on a ray boundary; view / code pointers are already offset to the chunk's first ray
     k_color_input<T><<<nblk(Mc * cols), 256, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, g.pe_w, c.cd->feat_dim,
-                                                       c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, pad);
+                                                       c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, pad, n.rot0);
     LAUNCHED("colour input");
     for (int l = 0; l < n.L - 1; ++l) {
         EpiRelu<T> e{};
@@ -967,7 +1097,7 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
     int pp = 0;
     for (l = n.L - 2; l >= 0; --l) {
         const int64_t ldin = l == 0 ? b.ldx : b.ldc;
-        RUN(wgrad<T>(c, P, b.ldc, b.C[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+        RUN(wgrad<T>(c, P, b.ldc, b.C[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, l == 0 ? n.rot0 : 0));
         RUN(colsum<T>(c, P, b.ldc, nullptr, 0, Mc, n.out[l], gr->db[l]));
         if (l > 0) {
             T* Pn = b.dC[pp ^ 1];
@@ -979,7 +1109,7 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
             EpiColorIn<T> e{};
             e.n_off = 0; e.nc = g.nc; e.fc = g.fc; e.F = c.cd->feat_dim; e.cc = g.cc; e.cd = c.cd->code_dim;
             e.dn = b.dn_color; e.Dout = b.Dout; e.ldo = b.ldo; e.feat_col0 = kIsBf16<T> ? 0 : 1;
-            e.dcode = b.dcode; e.ldc = c.cd->code_dim;
+            e.dcode = b.dcode; e.ldc = c.cd->code_dim; e.rot = n.rot0; e.in0 = g.in0;
             RUN((gemm_nn<T>(c, n, l, P, b.ldc, Mc, e, "colour input dgrad")));
         }
     }
@@ -1105,7 +1235,7 @@ int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int
     carve<T>(c, (chunk + 127) / 128 * 128, mode, workspace, &b, &c.sn, &c.cn);
     if (kIsBf16<T>) {
         RUN(prep_weights(c, c.sn, 1));
-        if (c.has_color) RUN(prep_weights(c, c.cn, 0));
+        if (c.has_color) { c.cn.rot0 = c.cg.fc; RUN(prep_weights(c, c.cn, 0)); }
     }
     const bool with_grad = mode == MSDF_MODE_FORWARD && (grad != nullptr);
     MSDF_CHECK_ARG(!(kIsBf16<T> && feat != nullptr), "%s: the raw feature output is only available in fp32 mode", who);
@@ -1114,7 +1244,7 @@ int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int
         const float* xc = x + 3 * m0;
         RUN(encode_chunk<T>(c, b, xc, Mc, with_grad));
         T* featc = nullptr; int64_t ldf_ = 0;
-        if (c.has_color) { featc = b.X + c.cg.fc; ldf_ = b.ldx; }
+        if (c.has_color) { featc = b.X + (kIsBf16<T> ? 0 : c.cg.fc); ldf_ = b.ldx; }
         else if (feat != nullptr) { featc = reinterpret_cast<T*>(feat + m0 * ld_feat); ldf_ = ld_feat; }
         RUN(forward_sweep<T>(c, b, Mc, featc, ldf_));
         if (with_grad) RUN(reverse_sweep<T>(c, b, Mc));
@@ -1145,7 +1275,7 @@ int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, in
     carve<T>(c, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, workspace, &b, &c.sn, &c.cn);
     if (kIsBf16<T>) {
         RUN(prep_weights(c, c.sn, 1));
-        if (c.has_color) RUN(prep_weights(c, c.cn, 0));
+        if (c.has_color) { c.cn.rot0 = c.cg.fc; RUN(prep_weights(c, c.cn, 0)); }
     }
     const int out_last = c.sn.out[c.sn.L - 1];
     const int feat_w = out_last - 1;
@@ -1155,7 +1285,7 @@ int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, in
         const float* xc = x + 3 * m0;
         // ---- recompute the chunk
         RUN(encode_chunk<T>(c, b, xc, Mc, true));
-        RUN(forward_sweep<T>(c, b, Mc, c.has_color ? b.X + c.cg.fc : nullptr, c.has_color ? b.ldx : 0));
+        RUN(forward_sweep<T>(c, b, Mc, c.has_color ? b.X + (kIsBf16<T> ? 0 : c.cg.fc) : nullptr, c.has_color ? b.ldx : 0));
         RUN(reverse_sweep<T>(c, b, Mc));
         RUN(decode_chunk<T>(c, b, xc, Mc, true, b.sdfc, b.gradc, b.mask));
         if (c.has_color) {

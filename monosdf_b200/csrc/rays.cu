@@ -26,8 +26,8 @@ __global__ void k_camera_rays(const float* __restrict__ uv, const float* __restr
 
 extern "C" int msdf_camera_rays(const float* uv, const float* pose, const float* intrinsics, int64_t batch, int64_t n_pixels,
                                 float* ray_dirs, float* cam_loc, void* stream) {
-    MSDF_CHECK_ARG(uv && pose && intrinsics && ray_dirs && cam_loc, "msdf_camera_rays: null pointer");
     if (batch * n_pixels == 0) return MSDF_OK;
+    MSDF_CHECK_ARG(uv && pose && intrinsics && ray_dirs && cam_loc, "msdf_camera_rays: null pointer");
     k_camera_rays<<<(unsigned)msdf_div_up(batch * n_pixels, 256), 256, 0, (cudaStream_t)stream>>>(uv, pose, intrinsics, batch, n_pixels,
                                                                                                 ray_dirs, cam_loc);
     MSDF_COUNT_LAUNCH();

@@ -199,11 +199,11 @@ extern "C" int msdf_render_forward(const float* z_vals, const float* sdf, const 
                                    int n_samples, const float* beta, const float* depth_scale, int64_t depth_scale_stride,
                                    const float* pose, int pose_per_ray, int white_bkgd, const float* bg_color, float* weights,
                                    float* rgb_values, float* depth_values, float* normal_map, void* stream) {
+    if (n_rays == 0) return MSDF_OK;
     MSDF_CHECK_ARG(z_vals && sdf && rgb && grad && beta && depth_scale && pose && weights && rgb_values && depth_values && normal_map,
                    "msdf_render_forward: null pointer");
     MSDF_CHECK_ARG(n_samples >= 1, "msdf_render_forward: n_samples=%d", n_samples);
     MSDF_CHECK_ARG(!white_bkgd || bg_color, "msdf_render_forward: bg_color required with white_bkgd");
-    if (n_rays == 0) return MSDF_OK;
     k_render_forward<<<(unsigned)msdf_div_up(n_rays, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(
         z_vals, sdf, rgb, grad, n_rays, n_samples, beta, depth_scale, depth_scale_stride, pose, pose_per_ray, white_bkgd, bg_color,
         weights, rgb_values, depth_values, normal_map);
@@ -218,10 +218,10 @@ extern "C" int msdf_render_backward(const float* z_vals, const float* sdf, const
                                     const float* d_weights, const float* d_rgb_values, const float* d_depth_values,
                                     const float* d_normal_map, float* d_sdf, float* d_rgb, float* d_grad, float* d_beta,
                                     void* stream) {
+    if (n_rays == 0) return MSDF_OK;
     MSDF_CHECK_ARG(z_vals && sdf && rgb && grad && beta && depth_scale && pose && d_sdf, "msdf_render_backward: null pointer");
     MSDF_CHECK_ARG(n_samples >= 1, "msdf_render_backward: n_samples=%d", n_samples);
     MSDF_CHECK_ARG(!white_bkgd || bg_color, "msdf_render_backward: bg_color required with white_bkgd");
-    if (n_rays == 0) return MSDF_OK;
     const size_t smem = (size_t)kWarps * 3 * n_samples * sizeof(float);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_render_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

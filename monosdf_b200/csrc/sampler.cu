@@ -316,9 +316,9 @@ int set_smem(K kernel, size_t bytes, const char* name) {
 extern "C" int msdf_sampler_init(const float* ray_o, const float* ray_d, int64_t n_rays, const float* t_vals,
                                  const float* t_rand, int n0, float bound, float near_, float far_max,
                                  float beta_coef, float* z, int cap, float* beta, float* pts, void* stream) {
+    if (n_rays == 0) return MSDF_OK;
     MSDF_CHECK_ARG(ray_o && ray_d && t_vals && z && beta && pts, "msdf_sampler_init: null pointer");
     MSDF_CHECK_ARG(n0 >= 2 && cap >= n0, "msdf_sampler_init: need 2 <= n0 <= cap (n0=%d cap=%d)", n0, cap);
-    if (n_rays == 0) return MSDF_OK;
     size_t smem = (size_t)kWarpsPerBlock * 2 * n0 * sizeof(float);
     int rc = set_smem(k_sampler_init, smem, "msdf_sampler_init"); if (rc) return rc;
     k_sampler_init<<<(unsigned)msdf_div_up(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
@@ -331,11 +331,11 @@ extern "C" int msdf_sampler_init(const float* ray_o, const float* ray_d, int64_t
 extern "C" int msdf_sampler_round(int64_t n_rays, int n_old, int n_new, float* z, float* sdf, const float* z_new,
                                   const float* sdf_new, int cap, const float* beta0, float eps, int beta_iters, float* beta,
                                   unsigned int* flag, void* stream) {
+    if (n_rays == 0) return MSDF_OK;
     MSDF_CHECK_ARG(z && sdf && sdf_new && beta && flag && beta0, "msdf_sampler_round: null pointer");
     MSDF_CHECK_ARG(n_old >= 0 && n_new >= 1 && n_old + n_new <= cap && n_old + n_new >= 2,
                    "msdf_sampler_round: bad sizes n_old=%d n_new=%d cap=%d", n_old, n_new, cap);
     MSDF_CHECK_ARG(n_old == 0 || z_new, "msdf_sampler_round: z_new required when n_old > 0");
-    if (n_rays == 0) return MSDF_OK;
     size_t smem = (size_t)kWarpsPerBlock * 4 * cap * sizeof(float);
     int rc = set_smem(k_sampler_round, smem, "msdf_sampler_round"); if (rc) return rc;
     k_sampler_round<<<(unsigned)msdf_div_up(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
@@ -348,9 +348,9 @@ extern "C" int msdf_sampler_round(int64_t n_rays, int n_old, int n_new, float* z
 extern "C" int msdf_sampler_upsample(int64_t n_rays, int n, const float* z, const float* sdf, int cap,
                                      const float* beta, float add_tiny, const float* u, int n_new, const float* ray_o,
                                      const float* ray_d, float* z_new, float* pts_new, void* stream) {
+    if (n_rays == 0) return MSDF_OK;
     MSDF_CHECK_ARG(z && sdf && beta && u && ray_o && ray_d && z_new && pts_new, "msdf_sampler_upsample: null pointer");
     MSDF_CHECK_ARG(n >= 2 && n <= cap && n_new >= 1, "msdf_sampler_upsample: bad sizes n=%d cap=%d n_new=%d", n, cap, n_new);
-    if (n_rays == 0) return MSDF_OK;
     size_t smem = (size_t)kWarpsPerBlock * (4 * (cap + 1) + n_new) * sizeof(float);
     int rc = set_smem(k_sampler_upsample, smem, "msdf_sampler_upsample"); if (rc) return rc;
     k_sampler_upsample<<<(unsigned)msdf_div_up(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
@@ -364,11 +364,11 @@ extern "C" int msdf_sampler_finalize(int64_t n_rays, int n, const float* z, cons
                                      const float* beta, const float* u, int u_per_ray, int n_s, const int32_t* pick,
                                      int n_extra, float near_, float far_, const int64_t* eik_idx, float* z_out,
                                      float* z_eik, void* stream) {
+    if (n_rays == 0) return MSDF_OK;
     MSDF_CHECK_ARG(z && sdf && beta && u && z_out, "msdf_sampler_finalize: null pointer");
     MSDF_CHECK_ARG(n >= 2 && n <= cap && n_s >= 1 && n_extra >= 0, "msdf_sampler_finalize: bad sizes");
     MSDF_CHECK_ARG(n_extra == 0 || pick, "msdf_sampler_finalize: pick required when n_extra > 0");
     MSDF_CHECK_ARG(z_eik == nullptr || eik_idx, "msdf_sampler_finalize: eik_idx required with z_eik");
-    if (n_rays == 0) return MSDF_OK;
     size_t smem = (size_t)kWarpsPerBlock * (4 * (cap + 1) + 2 * (n_s + 2 + n_extra)) * sizeof(float);
     int rc = set_smem(k_sampler_finalize, smem, "msdf_sampler_finalize"); if (rc) return rc;
     k_sampler_finalize<<<(unsigned)msdf_div_up(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(

@@ -135,6 +135,131 @@ __host__ __device__ inline uint32_t instr_desc(int M, int N, int a_mn_major, int
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
+// ----------------------------------------------------------------------------------------------------------
+// Epilogue I/O: TMEM hands every thread one ROW of the tile (lane = row), but global memory wants a warp to touch
+// whole rows.  WarpIO transposes 32-row x 32-column blocks through a private, swizzled 4 KB shared-memory slot so
+// that every global load / store / atomic of the epilogue is coalesced (8 rows x 64 B per bf16 request, one full
+// 128-byte row per fp32 atomic request).
+// ----------------------------------------------------------------------------------------------------------
+struct WarpIO {
+    uint32_t slot;      // shared-memory address of this warp's 4 KB staging slot
+    int lane;
+    int64_t row0;       // global row of lane 0
+    int64_t M;          // rows of the problem (rows >= M are masked)
+
+    __device__ __forceinline__ int64_t row() const { return row0 + lane; }
+    __device__ __forceinline__ bool valid() const { return row0 + lane < M; }
+
+    // bf16 block: row r = 64 B = 4 pieces of 16 B; piece p of row r lives at r*64 + ((p ^ ((r >> 1) & 3)) * 16)
+    static __device__ __forceinline__ uint32_t off16(int r, int p) { return (uint32_t)(r * 64 + ((p ^ ((r >> 1) & 3)) << 4)); }
+
+    // out[j] = P[row(), n0 + j], j < 32 (rows >= M read as 0).  Requires 16-byte aligned P + n0, ld % 8 == 0.
+    __device__ __forceinline__ void load(const __nv_bfloat16* P, int64_t ld, int n0, float out[32]) const {
+        uint4 q[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2), p = lane & 3;
+            const int64_t gr = row0 + r;
+            q[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (gr < M) q[i] = *reinterpret_cast<const uint4*>(P + gr * ld + n0 + p * 8);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2), p = lane & 3;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + off16(r, p)), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            uint32_t w[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(slot + off16(lane, p)) : "memory");
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                out[p * 8 + 2 * j] = __uint_as_float(w[j] << 16);
+                out[p * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+            }
+        }
+        __syncwarp();
+    }
+
+    // P[row(), n0 + j] = v[j] for j < nvalid (<= 32); rows >= M are skipped
+    __device__ __forceinline__ void store(__nv_bfloat16* P, int64_t ld, int n0, const float v[32], int nvalid) const {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            uint32_t w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(v[p * 8 + 2 * j], v[p * 8 + 2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + off16(lane, p)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2), p = lane & 3;
+            const int64_t gr = row0 + r;
+            uint4 q;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(slot + off16(r, p)) : "memory");
+            if (gr < M) {
+                __nv_bfloat16* dst = P + gr * ld + n0 + p * 8;
+                if (p * 8 + 8 <= nvalid) {
+                    *reinterpret_cast<uint4*>(dst) = q;
+                } else if (p * 8 < nvalid) {   // the piece straddles the last valid column
+                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+                    for (int j = 0; j < nvalid - p * 8; ++j) {
+                        const uint16_t h = (uint16_t)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
+                        *reinterpret_cast<uint16_t*>(dst + j) = h;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // fp32 block [32][32]: element (r, c) at r*128 + ((c ^ r) & 31)*4  (row-wise and column-wise conflict free)
+    __device__ __forceinline__ void stage_f32(const float v[32]) const {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (uint32_t)(lane * 128 + (((c ^ lane) & 31) << 2))), "f"(v[c]) : "memory");
+        __syncwarp();
+    }
+    __device__ __forceinline__ float staged(int r) const {   // element (r, lane)
+        float x;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(slot + (uint32_t)(r * 128 + (((lane ^ r) & 31) << 2))) : "memory");
+        return x;
+    }
+
+    // atomicAdd(addr(row0 + r, c), v_r[c]) for every row below row_limit; addr returns nullptr for masked elements.
+    // One request per row: 32 lanes = 32 consecutive columns (coalesced when addr is contiguous in c).
+    template <class AddrFn>
+    __device__ __forceinline__ void atomic_add(const float v[32], int64_t row_limit, AddrFn addr) const {
+        stage_f32(v);
+        for (int r = 0; r < 32; ++r) {
+            const int64_t gr = row0 + r;
+            if (gr >= row_limit) break;
+            const float x = staged(r);
+            float* p = addr(gr, lane);
+            if (p != nullptr) atomicAdd(p, x);
+        }
+        __syncwarp();
+    }
+
+    // C[row, c0 + j] = (C[row, c0 + j] +) v[j] for jlo <= j < jhi and rows < M: fp32, one contiguous row per request
+    __device__ __forceinline__ void store_f32(float* C, int64_t ldc, int c0, const float v[32], int jlo, int jhi, bool accum) const {
+        stage_f32(v);
+        const bool on = lane >= jlo && lane < jhi;
+        for (int r = 0; r < 32; ++r) {
+            const int64_t gr = row0 + r;
+            if (gr >= M) break;
+            const float x = staged(r);
+            if (on) { float* p = C + gr * ldc + c0 + lane; *p = accum ? *p + x : x; }
+        }
+        __syncwarp();
+    }
+};
+
 // ----------------------------------------------------------------------------------------------------------
 // shared-memory carve-up
 // ----------------------------------------------------------------------------------------------------------
@@ -143,8 +268,11 @@ struct Barriers {
     uint32_t tmem_base, pad;
 };
 
-// Epilogue concept: __device__ void operator()(int64_t m, int n, const float v[8]) const  -- row m, columns n..n+7
-// (n % 8 == 0; columns at or beyond the functor's own N must be masked by the functor).
+constexpr uint32_t kSlotBytes = 4096;   // per epilogue warp
+
+// Epilogue concept:  __device__ void chunk(const WarpIO& io, int n0, float v[32]) const
+//   v[j] = accumulator of row io.row(), column n0 + j (n0 % 32 == 0); the functor masks columns beyond its own N and
+//   rows beyond io.M, and uses io.load / io.store / io.atomic_add for coalesced traffic.
 
 // ==========================================================================================================
 // C = epi(A W^T), weights resident
@@ -159,7 +287,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const uint32_t sW = base;                                   // KB blocks of [BN rows x 128 B]
     const uint32_t w_block = (uint32_t)BN * 128u;
     const uint32_t sA = sW + (uint32_t)KB * w_block;            // stages x 16 KB
-    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)KB * w_block + (size_t)stages * kStageBytesA);
+    const uint32_t sE = sA + (uint32_t)stages * kStageBytesA;   // kEpiWarps staging slots
+    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)KB * w_block + (size_t)stages * kStageBytesA + kEpiWarps * kSlotBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = (M + BM - 1) / BM;
 
@@ -229,14 +358,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
             mbar_wait(smem_u32(&bars->tfull[a]), aph);
             tc_fence_after();
-            const int64_t row = tile * BM + q * 32 + lane;
+            const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, tile * BM + q * 32, M};
             for (int c = half; c < chunks; c += 2) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u + (uint32_t)c * 32u, v);
-                if (row < M) {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) epi(row, c * 32 + g * 8, v + g * 8);
-                }
+                epi.chunk(io, c * 32, v);
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->tempty[a]));
@@ -262,7 +388,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     constexpr uint32_t kBox = 64 * 128;                          // 64 k-rows x 128 B
     const uint32_t nbx = 2, nby = (uint32_t)BJ / 64u;
     const uint32_t stage_bytes = (nbx + nby) * kBox;
-    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)stages * stage_bytes);
+    const uint32_t sE = base + (uint32_t)stages * stage_bytes;
+    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)stages * stage_bytes + kEpiWarps * kSlotBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i0 = blockIdx.x * 128, j0 = blockIdx.y * BJ;
     const int64_t r0 = (int64_t)blockIdx.z * rows_per_split;
@@ -323,12 +450,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int chunks = (BJ + 31) / 32;
         mbar_wait(smem_u32(&bars->tfull[0]), 0);
         tc_fence_after();
-        const int64_t row = i0 + q * 32 + lane;
+        const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)i0 + q * 32, (int64_t)1 << 40};
         for (int c = half; c < chunks; c += 2) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 32u, v);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) epi(row, j0 + c * 32 + g * 8, v + g * 8);
+            epi.chunk(io, j0 + c * 32, v);
         }
     }
     tc_fence_before();
@@ -391,10 +517,11 @@ int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __
     rc = make_map(&mW, W, BN, Kp, ldw, BN, what); if (rc) return rc;
     const int KB = Kp / 64;
     const size_t wbytes = (size_t)KB * BN * 128;
-    int stages = (int)((227 * 1024 - 1024 - sizeof(Barriers) - wbytes) / kStageBytesA);
+    const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes;
+    int stages = (int)((227 * 1024 - fixed - wbytes) / kStageBytesA);
     if (stages > 6) stages = 6;
     if (stages < 2) { msdf_set_error("%s: weights do not leave room for the A ring", what); return MSDF_ERR_ARG; }
-    const size_t smem = 1024 + wbytes + (size_t)stages * kStageBytesA + sizeof(Barriers);
+    const size_t smem = fixed + wbytes + (size_t)stages * kStageBytesA;
     static bool attr_set = false;   // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_gemm<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -429,9 +556,10 @@ int launch_wgrad(const __nv_bfloat16* X, int64_t ldx, int Ci, const __nv_bfloat1
     if (rps < 256) rps = 256;
     splits = (int)((M + rps - 1) / rps);
     const uint32_t stage_bytes = (2 + BJ / 64) * 64 * 128;
-    int stages = (int)((227 * 1024 - 1024 - sizeof(Barriers)) / stage_bytes);
+    const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes;
+    int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (stages > 6) stages = 6;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + sizeof(Barriers);
+    const size_t smem = fixed + (size_t)stages * stage_bytes;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_tc_wgrad<Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

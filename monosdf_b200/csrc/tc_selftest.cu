@@ -31,6 +31,17 @@ __global__ void k_ref_wgrad(const bf16* X, int64_t ldx, const bf16* Y, int64_t l
     for (int64_t m = 0; m < M; ++m) s = fmaf(__bfloat162float(X[m * ldx + i]), __bfloat162float(Y[m * ldy + j]), s);
     C[(int64_t)i * ldc + j] = s;
 }
+// expected result of the bf16-io epilogue: columns < N: bf16(ref + Cin); columns >= N: the sentinel already in Cb
+__global__ void k_ref_bf16(const float* ref, const bf16* Cin, const bf16* Cb, int64_t M, int N, int ldc, float* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * ldc) return;
+    const int n = (int)(i % ldc);
+    out[i] = n < N ? __bfloat162float(__float2bfloat16(ref[i] + __bfloat162float(Cin[i]))) : __bfloat162float(Cb[i]);
+}
+__global__ void k_bf16_to_f32(const bf16* a, float* b, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[i] = __bfloat162float(a[i]);
+}
 __global__ void k_maxerr(const float* a, const float* b, int64_t n, float* out) {   // out[0] = max |a-b|, out[1] = max |b|
     float e = 0.f, r = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -42,21 +53,34 @@ __global__ void k_maxerr(const float* a, const float* b, int64_t n, float* out) 
     atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(r));
 }
 
-struct EpiStore {
+struct EpiStore {     // C fp32: no coalescing helper for fp32 row stores; plain per-row writes are fine for a test
     float* C; int64_t ldc; int N;
-    __device__ __forceinline__ void operator()(int64_t m, int n, const float v[8]) const {
+    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32]) const {
+        if (!io.valid()) return;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (n + j < N) C[m * ldc + n + j] = v[j];
+        for (int j = 0; j < 32; ++j)
+            if (n0 + j < N) C[io.row() * ldc + n0 + j] = v[j];
+    }
+};
+struct EpiStoreBf16 {  // exercises WarpIO::load / store: C = bf16(acc + Cin)
+    __nv_bfloat16* C; const __nv_bfloat16* Cin; int64_t ldc; int N;
+    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32]) const {
+        const int nv = N - n0;
+        if (nv <= 0) return;
+        float a[32];
+        io.load(Cin, ldc, n0, a);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += a[j];
+        io.store(C, ldc, n0, v, nv < 32 ? nv : 32);
     }
 };
 struct EpiAtomicAdd {
     float* C; int64_t ldc; int Ni, Nj;
-    __device__ __forceinline__ void operator()(int64_t i, int n, const float v[8]) const {
-        if (i >= Ni) return;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (n + j < Nj) atomicAdd(C + i * ldc + n + j, v[j]);
+    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32]) const {
+        const int nv = Nj - n0;
+        if (nv <= 0) return;
+        float* Cp = C; const int64_t ld = ldc; const int nn = nv;
+        io.atomic_add(v, (int64_t)Ni, [=](int64_t r, int c) -> float* { return c < nn ? Cp + r * ld + n0 + c : nullptr; });
     }
 };
 
@@ -70,6 +94,8 @@ const Case kCases[] = {
     {1, 70001, 257, 39, 320, 64},
     {1, 300, 64, 256, 64, 256},
     {1, 262144, 256, 256, 256, 256},
+    {2, 128 * 40 + 19, 217, 256, 224, 256},   // kind 2: GEMM with the bf16 load / store epilogue (ragged N, ragged M)
+    {2, 70000, 256, 256, 256, 256},
 };
 }  // namespace
 
@@ -80,6 +106,31 @@ extern "C" int msdf_tc_selftest(int variant, float* result_host, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     bf16 *A = nullptr, *B = nullptr; float *C = nullptr, *R = nullptr, *out = nullptr;
     int rc = MSDF_OK;
+    if (c.kind == 2) {
+        const int64_t lda = c.Kp, ldw = c.Kp, ldc = 256;
+        bf16 *Cb = nullptr, *Ci = nullptr;
+        MSDF_CUDA_CALL(cudaMalloc(&A, c.M * lda * 2)); MSDF_CUDA_CALL(cudaMalloc(&B, (int64_t)c.Np * ldw * 2));
+        MSDF_CUDA_CALL(cudaMalloc(&Cb, c.M * ldc * 2)); MSDF_CUDA_CALL(cudaMalloc(&Ci, c.M * ldc * 2));
+        MSDF_CUDA_CALL(cudaMalloc(&C, c.M * ldc * 4)); MSDF_CUDA_CALL(cudaMalloc(&R, c.M * ldc * 4)); MSDF_CUDA_CALL(cudaMalloc(&out, 8));
+        k_fill<<<(unsigned)msdf_div_up(c.M * lda, 256), 256, 0, st>>>(A, c.M * lda, 1, 2.0f);
+        k_fill<<<(unsigned)msdf_div_up((int64_t)c.Np * ldw, 256), 256, 0, st>>>(B, (int64_t)c.Np * ldw, 2, 1.0f);
+        k_fill<<<(unsigned)msdf_div_up(c.M * ldc, 256), 256, 0, st>>>(Ci, c.M * ldc, 5, 4.0f);
+        k_fill<<<(unsigned)msdf_div_up(c.M * ldc, 256), 256, 0, st>>>(Cb, c.M * ldc, 6, 1.0f);   // sentinel beyond N must survive
+        MSDF_CUDA_CALL(cudaMemsetAsync(out, 0, 8, st));
+        k_ref_gemm<<<(unsigned)msdf_div_up(c.M * c.N, 256), 256, 0, st>>>(A, lda, B, ldw, c.M, c.N, c.Kp, R, ldc);
+        k_ref_bf16<<<(unsigned)msdf_div_up(c.M * ldc, 256), 256, 0, st>>>(R, Ci, Cb, c.M, c.N, (int)ldc, R);
+        EpiStoreBf16 e{Cb, Ci, ldc, c.N};
+        rc = msdf_tc::launch_gemm(A, lda, c.M, c.Kp, B, ldw, c.Np, e, st, "msdf_tc_selftest(gemm bf16 io)");
+        if (!rc) {
+            k_bf16_to_f32<<<(unsigned)msdf_div_up(c.M * ldc, 256), 256, 0, st>>>(Cb, C, c.M * ldc);
+            k_maxerr<<<256, 256, 0, st>>>(C, R, c.M * ldc, out);
+        }
+        cudaError_t e3 = cudaStreamSynchronize(st);
+        if (!rc && e3 != cudaSuccess) { msdf_set_error("msdf_tc_selftest: kernel failed: %s", cudaGetErrorString(e3)); rc = MSDF_ERR_CUDA; }
+        if (!rc) cudaMemcpy(result_host, out, 8, cudaMemcpyDeviceToHost);
+        cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(R); cudaFree(out); cudaFree(Cb); cudaFree(Ci);
+        return rc;
+    }
     if (c.kind == 0) {
         const int64_t lda = c.Kp, ldw = c.Kp, ldc = c.Np;
         MSDF_CUDA_CALL(cudaMalloc(&A, c.M * lda * 2)); MSDF_CUDA_CALL(cudaMalloc(&B, (int64_t)c.Np * ldw * 2));
