@@ -92,22 +92,28 @@ __device__ __forceinline__ void store_row(bf16* p, const float* v, int nv) {
         if (j < nv) p[j] = __float2bfloat16(v[j]);
 }
 
-// activation math.  FAST = bf16 mode: MUFU ex2/lg2 approximations (error far below bf16 resolution);
-// precise (libdevice) otherwise.
+// activation math.  FAST = bf16 mode: branch-free MUFU ex2/lg2 approximations with flush-to-zero (error far below
+// bf16 resolution; no denormal slow paths, no divergent branches in the GEMM epilogues); precise (libdevice) otherwise.
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float k100Log2e = 144.26950408889634f;       // 100 / ln 2
+constexpr float kLn2Over100 = 0.0069314718055994531f;  // ln 2 / 100
+
 template <bool FAST>
 __device__ __forceinline__ float softplus100(float p) {   // nn.Softplus(beta=100), threshold 20 (network.py:77)
+    // fast: max(p, 0) + log(1 + exp(-|100 p|)) / 100; past the threshold 1 + exp(.) rounds to 1, so the result is p
+    if (FAST) return fmaxf(p, 0.f) + fast_lg2(1.0f + fast_ex2(-fabsf(p) * k100Log2e)) * kLn2Over100;
     const float bp = 100.f * p;
-    if (FAST) return bp > 20.f ? p : fmaxf(p, 0.f) + __logf(1.0f + __expf(-fabsf(bp))) * 0.01f;
     return bp > 20.f ? p : log1pf(expf(bp)) / 100.f;
 }
 // sigmoid(100 p) from h = softplus100(p):  1 - exp(-100 h)
 template <bool FAST>
-__device__ __forceinline__ float sig_from_h(float h) { return FAST ? 1.0f - __expf(-100.f * h) : -expm1f(-100.f * h); }
+__device__ __forceinline__ float sig_from_h(float h) { return FAST ? 1.0f - fast_ex2(-k100Log2e * h) : -expm1f(-100.f * h); }
 // (sigmoid, 100 (1 - sigmoid)) from h; the second is exactly 0 past the softplus threshold like torch's double backward
 template <bool FAST>
 __device__ __forceinline__ void sig_dsig_from_h(float h, float& s, float& d) {
     const float t = 100.f * h;
-    const float e = FAST ? __expf(-t) : expf(-t);
+    const float e = FAST ? fast_ex2(-k100Log2e * h) : expf(-t);
     s = FAST ? 1.0f - e : -expm1f(-t);
     d = t > 20.f ? 0.f : 100.f * e;
 }
@@ -408,6 +414,8 @@ struct EpiBase {
     }
     // tcgen05 engine: number of valid columns of the 32-column chunk starting at n0 (<= 0: nothing to do)
     __device__ __forceinline__ int chunk_cols(int n0) const { const int nv = N - n0; return nv < 32 ? nv : 32; }
+    static constexpr int kPre = 0;                 // epilogues that read operands back override kPre / prefetch
+    __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
 };
 
 using msdf_tc::WarpIO;
@@ -421,7 +429,7 @@ struct EpiFwdAct : EpiBase<EpiFwdAct<T>> {   // out[m,n] = softplus100(acc + b[n
         for (int j = 0; j < W; ++j) o[j] = j < nv ? softplus100<kIsBf16<T>>(v[j] + __ldg(bias + n + j)) * oscale : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
 #pragma unroll
@@ -438,7 +446,7 @@ struct EpiBias : EpiBase<EpiBias<T>> {       // out[m,n] = acc + b[n]
         for (int j = 0; j < W; ++j) o[j] = j < nv ? v[j] + __ldg(bias + n + j) : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
 #pragma unroll
@@ -455,7 +463,7 @@ struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
         for (int j = 0; j < W; ++j) o[j] = j < nv ? fmaxf(v[j] + __ldg(bias + n + j), 0.f) : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
 #pragma unroll
@@ -476,7 +484,7 @@ struct EpiAtomic : EpiBase<EpiAtomic> {
         for (int j = 0; j < W; ++j)
             if (j < nv) atomicAdd(o + j, v[j]);
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         const EpiAtomic e = *this;
@@ -516,7 +524,7 @@ struct EpiRev : EpiBase<EpiRev<T>> {
             else stf(Aout + m * lda + c, r * sig_from_h<kIsBf16<T>>(ldf(Hin + m * ldh + c) * hscale));
         }
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         if (layer0) {                              // everything is d sdf / d h0
@@ -534,11 +542,15 @@ struct EpiRev : EpiBase<EpiRev<T>> {
         }
         if (nh > 0) {
             float h[32];
-            io.load(Hin, ldh, n0, h);
+            io.unstage(q, h);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(h[j] * hscale);
             io.store(Aout, lda, n0, v, nh);
         }
+    }
+    static constexpr int kPre = 1;
+    __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
+        if (!layer0 && n0 < dh && n0 < this->N) io.prefetch(Hin, ldh, n0, q);
     }
 };
 // tangent sweep, layer l: acc = (t_l W_l^T)[m,n], n over the layer's outputs
@@ -561,12 +573,12 @@ struct EpiTan : EpiBase<EpiTan<T>> {
         store_row<W>(Tout + m * ldt + n, t, nv);
         store_row<W>(AZ + m * lda + n, z, nv);
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         float h[32], z[32];
-        io.load(Hn, ldh, n0, h);
-        io.load(AZ, lda, n0, z);
+        io.unstage(q, h);
+        io.unstage(q + 4, z);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float s, d;
@@ -576,6 +588,10 @@ struct EpiTan : EpiBase<EpiTan<T>> {
         }
         io.store(Tout, ldt, n0, v, nv);
         io.store(AZ, lda, n0, z, nv);
+    }
+    static constexpr int kPre = 2;
+    __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
+        if (n0 < this->N) { io.prefetch(Hn, ldh, n0, q); io.prefetch(AZ, lda, n0, q + 4); }
     }
 };
 // backward sweep, layer l: acc = (pbar_l W_l)[m,n], n over the layer's inputs
@@ -605,7 +621,7 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
             else { T* p = PZ + m * ldp + c; stf(p, r * sig_from_h<kIsBf16<T>>(ldf(Hin + m * ldh + c) * hscale) + ldf(p)); }
         }
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         if (layer0) {
@@ -624,12 +640,16 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
         }
         if (nh > 0) {
             float h[32], z[32];
-            io.load(Hin, ldh, n0, h);
-            io.load(PZ, ldp, n0, z);
+            io.unstage(q, h);
+            io.unstage(q + 4, z);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(h[j] * hscale) + z[j];
             io.store(PZ, ldp, n0, v, nh);
         }
+    }
+    static constexpr int kPre = 2;
+    __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
+        if (!layer0 && n0 < dh && n0 < this->N) { io.prefetch(Hin, ldh, n0, q); io.prefetch(PZ, ldp, n0, q + 4); }
     }
 };
 template <class T>
@@ -642,14 +662,18 @@ struct EpiBwdRelu : EpiBase<EpiBwdRelu<T>> {  // colour net dgrad: out[m,n] = ac
         for (int j = 0; j < W; ++j) o[j] = h[j] > 0.f ? v[j] : 0.f;
         store_row<W>(out + m * ldo + n, o, nv);
     }
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         float h[32];
-        io.load(Hin, ldh, n0, h);
+        io.unstage(q, h);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
         io.store(out, ldo, n0, v, nv);
+    }
+    static constexpr int kPre = 1;
+    __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
+        if (n0 < this->N) io.prefetch(Hin, ldh, n0, q);
     }
 };
 // colour net layer-0 dgrad: route d(input) columns to the SDF net's adjoints
@@ -671,7 +695,7 @@ struct EpiColorIn : EpiBase<EpiColorIn<T>> {
         }
     }
     // bf16 mode: the input is stored rotated so that feat starts at column 0 -> whole chunks of feat columns
-    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32]) const {
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         const int g0c = n0 + n_off;                // first rotated column of the chunk

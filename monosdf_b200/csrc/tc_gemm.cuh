@@ -154,16 +154,20 @@ struct WarpIO {
     // bf16 block: row r = 64 B = 4 pieces of 16 B; piece p of row r lives at r*64 + ((p ^ ((r >> 1) & 3)) * 16)
     static __device__ __forceinline__ uint32_t off16(int r, int p) { return (uint32_t)(r * 64 + ((p ^ ((r >> 1) & 3)) << 4)); }
 
-    // out[j] = P[row(), n0 + j], j < 32 (rows >= M read as 0).  Requires 16-byte aligned P + n0, ld % 8 == 0.
-    __device__ __forceinline__ void load(const __nv_bfloat16* P, int64_t ld, int n0, float out[32]) const {
-        uint4 q[4];
+    // Coalesced read of the 32 x 32 bf16 block P[row0.., n0..n0+31] in two steps so that the global latency can be
+    // hidden: prefetch() issues the loads (lane t fetches 16-byte piece t&3 of rows i*8 + t/4), unstage() transposes
+    // them through the slot so that out[j] = P[row(), n0 + j] (rows >= M read as 0).
+    // Requires 16-byte aligned P + n0 and ld % 8 == 0.
+    __device__ __forceinline__ void prefetch(const __nv_bfloat16* P, int64_t ld, int n0, uint4 q[4]) const {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = i * 8 + (lane >> 2), p = lane & 3;
             const int64_t gr = row0 + r;
             q[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (gr < M) q[i] = *reinterpret_cast<const uint4*>(P + gr * ld + n0 + p * 8);
+            if (gr < M) q[i] = __ldg(reinterpret_cast<const uint4*>(P + gr * ld + n0 + p * 8));
         }
+    }
+    __device__ __forceinline__ void unstage(const uint4 q[4], float out[32]) const {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = i * 8 + (lane >> 2), p = lane & 3;
@@ -181,6 +185,11 @@ struct WarpIO {
             }
         }
         __syncwarp();
+    }
+    __device__ __forceinline__ void load(const __nv_bfloat16* P, int64_t ld, int n0, float out[32]) const {
+        uint4 q[4];
+        prefetch(P, ld, n0, q);
+        unstage(q, out);
     }
 
     // P[row(), n0 + j] = v[j] for j < nvalid (<= 32); rows >= M are skipped
@@ -270,9 +279,16 @@ struct Barriers {
 
 constexpr uint32_t kSlotBytes = 4096;   // per epilogue warp
 
-// Epilogue concept:  __device__ void chunk(const WarpIO& io, int n0, float v[32]) const
-//   v[j] = accumulator of row io.row(), column n0 + j (n0 % 32 == 0); the functor masks columns beyond its own N and
-//   rows beyond io.M, and uses io.load / io.store / io.atomic_add for coalesced traffic.
+// Epilogue concept:
+//   static constexpr int kPre                                   number of bf16 operands the epilogue reads back (0..2)
+//   void prefetch(const WarpIO& io, int n0, uint4* q) const     issue their global loads into q[4 * kPre] (no waiting);
+//                                                               called for all of the warp's chunks BEFORE the
+//                                                               accumulator is awaited, so the loads overlap the MMAs
+//   void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const
+//        v[j] = accumulator of row io.row(), column n0 + j (n0 % 32 == 0); the functor masks columns beyond its own N
+//        and rows beyond io.M, and uses io.unstage / io.store / io.atomic_add for coalesced traffic.
+template <class Epi> constexpr int pre_regs() { return Epi::kPre > 0 ? 4 * Epi::kPre : 1; }
+constexpr int kMaxChunksPerWarp = 4;   // 256 accumulator columns / 32 / 2 warps per TMEM lane quadrant
 
 // ==========================================================================================================
 // C = epi(A W^T), weights resident
@@ -356,13 +372,23 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         uint32_t it = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+            const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, tile * BM + q * 32, M};
+            uint4 pre[kMaxChunksPerWarp][pre_regs<Epi>()];
+            if (Epi::kPre > 0) {
+#pragma unroll
+                for (int i = 0; i < kMaxChunksPerWarp; ++i)
+                    if (half + 2 * i < chunks) epi.prefetch(io, (half + 2 * i) * 32, pre[i]);
+            }
             mbar_wait(smem_u32(&bars->tfull[a]), aph);
             tc_fence_after();
-            const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, tile * BM + q * 32, M};
-            for (int c = half; c < chunks; c += 2) {
-                float v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u + (uint32_t)c * 32u, v);
-                epi.chunk(io, c * 32, v);
+#pragma unroll
+            for (int i = 0; i < kMaxChunksPerWarp; ++i) {
+                const int c = half + 2 * i;
+                if (c < chunks) {
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u + (uint32_t)c * 32u, v);
+                    epi.chunk(io, c * 32, v, pre[i]);
+                }
             }
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->tempty[a]));
@@ -454,7 +480,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         for (int c = half; c < chunks; c += 2) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 32u, v);
-            epi.chunk(io, j0 + c * 32, v);
+            epi.chunk(io, j0 + c * 32, v, nullptr);
         }
     }
     tc_fence_before();

@@ -55,7 +55,9 @@ __global__ void k_maxerr(const float* a, const float* b, int64_t n, float* out) 
 
 struct EpiStore {     // C fp32: no coalescing helper for fp32 row stores; plain per-row writes are fine for a test
     float* C; int64_t ldc; int N;
-    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32]) const {
+    static constexpr int kPre = 0;
+    __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
+    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
         if (!io.valid()) return;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -64,11 +66,13 @@ struct EpiStore {     // C fp32: no coalescing helper for fp32 row stores; plain
 };
 struct EpiStoreBf16 {  // exercises WarpIO::load / store: C = bf16(acc + Cin)
     __nv_bfloat16* C; const __nv_bfloat16* Cin; int64_t ldc; int N;
-    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32]) const {
+    static constexpr int kPre = 1;
+    __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO& io, int n0, uint4* q) const { if (n0 < N) io.prefetch(Cin, ldc, n0, q); }
+    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = N - n0;
         if (nv <= 0) return;
         float a[32];
-        io.load(Cin, ldc, n0, a);
+        io.unstage(q, a);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += a[j];
         io.store(C, ldc, n0, v, nv < 32 ? nv : 32);
@@ -76,7 +80,9 @@ struct EpiStoreBf16 {  // exercises WarpIO::load / store: C = bf16(acc + Cin)
 };
 struct EpiAtomicAdd {
     float* C; int64_t ldc; int Ni, Nj;
-    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32]) const {
+    static constexpr int kPre = 0;
+    __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
+    __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = Nj - n0;
         if (nv <= 0) return;
         float* Cp = C; const int64_t ld = ldc; const int nn = nv;
