@@ -416,6 +416,7 @@ struct EpiBase {
     __device__ __forceinline__ int chunk_cols(int n0) const { const int nv = N - n0; return nv < 32 ? nv : 32; }
     static constexpr int kPre = 0;                 // epilogues that read operands back override kPre / prefetch
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
+    __device__ __forceinline__ const float* colvec() const { return nullptr; }
 };
 
 using msdf_tc::WarpIO;
@@ -433,9 +434,17 @@ struct EpiFwdAct : EpiBase<EpiFwdAct<T>> {   // out[m,n] = softplus100(acc + b[n
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < nv ? softplus100<true>(v[j] + __ldg(bias + n0 + j)) * oscale : 0.f;
+        float b[32];
+        io.colvec(n0, b);
+        const float os = oscale, c2 = kLn2Over100 * oscale;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {          // softplus100(p) * oscale, branch free (see softplus100<true>)
+            const float p = v[j] + b[j];
+            v[j] = fmaf(fast_lg2(1.0f + fast_ex2(-fabsf(p) * k100Log2e)), c2, fmaxf(p, 0.f) * os);
+        }
         io.store(out, ldo, n0, v, nv);
     }
+    __device__ __forceinline__ const float* colvec() const { return bias; }
 };
 template <class T>
 struct EpiBias : EpiBase<EpiBias<T>> {       // out[m,n] = acc + b[n]
@@ -450,9 +459,13 @@ struct EpiBias : EpiBase<EpiBias<T>> {       // out[m,n] = acc + b[n]
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < nv ? v[j] + __ldg(bias + n0 + j) : 0.f;
+        float b[32];
+        io.colvec(n0, b);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += b[j];
         io.store(out, ldo, n0, v, nv);
     }
+    __device__ __forceinline__ const float* colvec() const { return bias; }
 };
 template <class T>
 struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
@@ -467,9 +480,13 @@ struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = j < nv ? fmaxf(v[j] + __ldg(bias + n0 + j), 0.f) : 0.f;
+        float b[32];
+        io.colvec(n0, b);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b[j], 0.f);
         io.store(out, ldo, n0, v, nv);
     }
+    __device__ __forceinline__ const float* colvec() const { return bias; }
 };
 // C[row(m), n] += acc  (split-K weight gradients).  With perm_rows > 0 the GEMM's row index i addresses the
 // permuted last layer [features..., sdf]: i < perm_rows - 1 -> row i + 1, i == perm_rows - 1 -> row 0.

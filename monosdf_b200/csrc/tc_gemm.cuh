@@ -119,6 +119,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split form: issue the load, later wait for it.  The wait names the registers as read-write operands so that every
+// consumer of r[] is ordered after it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t r[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
 // shared-memory matrix descriptors (cute::UMMA::SmemDescriptor): SWIZZLE_128B, Blackwell version bit
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -147,6 +171,15 @@ struct WarpIO {
     int lane;
     int64_t row0;       // global row of lane 0
     int64_t M;          // rows of the problem (rows >= M are masked)
+    uint32_t cvec;      // shared-memory address of the CTA's per-column vector (bias), zero padded to 256 entries
+
+    // b[j] = column vector entry n0 + j: 8 broadcast 16-byte shared loads (every lane reads the same address)
+    __device__ __forceinline__ void colvec(int n0, float b[32]) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b[4 * i]), "=f"(b[4 * i + 1]), "=f"(b[4 * i + 2]), "=f"(b[4 * i + 3])
+                         : "r"(cvec + (uint32_t)(n0 + 4 * i) * 4u));
+    }
 
     __device__ __forceinline__ int64_t row() const { return row0 + lane; }
     __device__ __forceinline__ bool valid() const { return row0 + lane < M; }
@@ -278,12 +311,15 @@ struct Barriers {
 };
 
 constexpr uint32_t kSlotBytes = 4096;   // per epilogue warp
+constexpr uint32_t kColVecBytes = 1024;
 
 // Epilogue concept:
 //   static constexpr int kPre                                   number of bf16 operands the epilogue reads back (0..2)
 //   void prefetch(const WarpIO& io, int n0, uint4* q) const     issue their global loads into q[4 * kPre] (no waiting);
 //                                                               called for all of the warp's chunks BEFORE the
 //                                                               accumulator is awaited, so the loads overlap the MMAs
+//   const float* colvec() const                                 per-column vector (bias, N entries) or nullptr; the kernel
+//                                                               stages it in shared memory once, read with io.colvec()
 //   void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const
 //        v[j] = accumulator of row io.row(), column n0 + j (n0 % 32 == 0); the functor masks columns beyond its own N
 //        and rows beyond io.M, and uses io.unstage / io.store / io.atomic_add for coalesced traffic.
@@ -304,7 +340,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const uint32_t w_block = (uint32_t)BN * 128u;
     const uint32_t sA = sW + (uint32_t)KB * w_block;            // stages x 16 KB
     const uint32_t sE = sA + (uint32_t)stages * kStageBytesA;   // kEpiWarps staging slots
-    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)KB * w_block + (size_t)stages * kStageBytesA + kEpiWarps * kSlotBytes);
+    const uint32_t sV = sE + kEpiWarps * kSlotBytes;            // per-column vector (bias), 256 floats
+    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)KB * w_block + (size_t)stages * kStageBytesA + kEpiWarps * kSlotBytes + kColVecBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = (M + BM - 1) / BM;
 
@@ -317,6 +354,14 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
+    if (threadIdx.x >= 64) {                                    // epilogue warps stage the column vector
+        const float* cv = epi.colvec();
+        const int j = (int)threadIdx.x - 64;
+        if (j < 256) {
+            const float x = (cv != nullptr && j < epi.N) ? __ldg(cv + j) : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sV + (uint32_t)j * 4u), "f"(x) : "memory");
+        }
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -370,24 +415,57 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int chunks = (BN + 31) / 32;
         uint32_t it = 0;
+        uint4 pre[Epi::kPre == 1 ? 4 : (Epi::kPre == 2 ? 2 : 1)][pre_regs<Epi>()];
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
-            const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, tile * BM + q * 32, M};
-            uint4 pre[kMaxChunksPerWarp][pre_regs<Epi>()];
-            if (Epi::kPre > 0) {
+            const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, tile * BM + q * 32, M, sV};
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u;
+            if (Epi::kPre == 0) {
+                mbar_wait(smem_u32(&bars->tfull[a]), aph);
+                tc_fence_after();
+                // accumulator chunks double buffered in registers: the TMEM load of chunk i+1 overlaps the math of chunk i
+                uint32_t r[2][32];
+                if (half < chunks) tmem_ld32_issue(tacc + (uint32_t)half * 32u, r[0]);
 #pragma unroll
-                for (int i = 0; i < kMaxChunksPerWarp; ++i)
-                    if (half + 2 * i < chunks) epi.prefetch(io, (half + 2 * i) * 32, pre[i]);
-            }
-            mbar_wait(smem_u32(&bars->tfull[a]), aph);
-            tc_fence_after();
+                for (int i = 0; i < kMaxChunksPerWarp; ++i) {
+                    const int c = half + 2 * i;
+                    if (c < chunks) {
+                        tmem_ld32_wait(r[i & 1]);
+                        if (c + 2 < chunks && i + 1 < kMaxChunksPerWarp) tmem_ld32_issue(tacc + (uint32_t)(c + 2) * 32u, r[(i + 1) & 1]);
+                        float v[32];
 #pragma unroll
-            for (int i = 0; i < kMaxChunksPerWarp; ++i) {
-                const int c = half + 2 * i;
-                if (c < chunks) {
-                    float v[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u + (uint32_t)c * 32u, v);
-                    epi.chunk(io, c * 32, v, pre[i]);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[i & 1][j]);
+                        epi.chunk(io, c * 32, v, nullptr);
+                    }
+                }
+            } else {
+                // Rolling prefetch of the epilogue's bf16 operands, kDepth chunks ahead (across tile boundaries): the
+                // registers of a consumed chunk are refilled at once with the loads of chunk + kDepth, so global latency
+                // is covered by the math / stores of the chunks in between and never by an idle warp.
+                constexpr int kDepth = Epi::kPre == 1 ? 4 : 2;
+                if (it == 0) {
+#pragma unroll
+                    for (int i = 0; i < kDepth; ++i)
+                        if (half + 2 * i < chunks) epi.prefetch(io, (half + 2 * i) * 32, pre[i]);
+                }
+                const bool has_next = tile + gridDim.x < num_tiles;
+                const WarpIO io_next{io.slot, lane, (tile + gridDim.x) * BM + q * 32, M, sV};
+                mbar_wait(smem_u32(&bars->tfull[a]), aph);
+                tc_fence_after();
+#pragma unroll
+                for (int i = 0; i < kMaxChunksPerWarp; ++i) {
+                    const int c = half + 2 * i;
+                    if (c < chunks) {
+                        float v[32];
+                        tmem_ld32(tacc + (uint32_t)c * 32u, v);
+                        epi.chunk(io, c * 32, v, pre[i % kDepth]);
+                    }
+                    const int jn = i + kDepth;                 // chunk slot that reuses these registers
+                    if (jn < kMaxChunksPerWarp) {
+                        if (half + 2 * jn < chunks) epi.prefetch(io, (half + 2 * jn) * 32, pre[i % kDepth]);
+                    } else if (has_next && half + 2 * (jn - kMaxChunksPerWarp) < chunks) {
+                        epi.prefetch(io_next, (half + 2 * (jn - kMaxChunksPerWarp)) * 32, pre[i % kDepth]);
+                    }
                 }
             }
             tc_fence_before();
@@ -476,7 +554,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int chunks = (BJ + 31) / 32;
         mbar_wait(smem_u32(&bars->tfull[0]), 0);
         tc_fence_after();
-        const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)i0 + q * 32, (int64_t)1 << 40};
+        const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)i0 + q * 32, (int64_t)1 << 40, 0u};
         for (int c = half; c < chunks; c += 2) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 32u, v);
@@ -543,7 +621,7 @@ int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __
     rc = make_map(&mW, W, BN, Kp, ldw, BN, what); if (rc) return rc;
     const int KB = Kp / 64;
     const size_t wbytes = (size_t)KB * BN * 128;
-    const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes;
+    const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes + kColVecBytes;
     int stages = (int)((227 * 1024 - fixed - wbytes) / kStageBytesA);
     if (stages > 6) stages = 6;
     if (stages < 2) { msdf_set_error("%s: weights do not leave room for the A ring", what); return MSDF_ERR_ARG; }

@@ -57,6 +57,7 @@ struct EpiStore {     // C fp32: no coalescing helper for fp32 row stores; plain
     float* C; int64_t ldc; int N;
     static constexpr int kPre = 0;
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
+    __device__ __forceinline__ const float* colvec() const { return nullptr; }
     __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
         if (!io.valid()) return;
 #pragma unroll
@@ -68,6 +69,7 @@ struct EpiStoreBf16 {  // exercises WarpIO::load / store: C = bf16(acc + Cin)
     __nv_bfloat16* C; const __nv_bfloat16* Cin; int64_t ldc; int N;
     static constexpr int kPre = 1;
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO& io, int n0, uint4* q) const { if (n0 < N) io.prefetch(Cin, ldc, n0, q); }
+    __device__ __forceinline__ const float* colvec() const { return nullptr; }
     __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = N - n0;
         if (nv <= 0) return;
@@ -82,6 +84,7 @@ struct EpiAtomicAdd {
     float* C; int64_t ldc; int Ni, Nj;
     static constexpr int kPre = 0;
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
+    __device__ __forceinline__ const float* colvec() const { return nullptr; }
     __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = Nj - n0;
         if (nv <= 0) return;
