@@ -52,10 +52,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)      // suspend-time hint (ns): the waiting warp sleeps instead of spinning
         : "memory");
     return ok != 0;
 }
@@ -172,6 +172,25 @@ struct WarpIO {
     int64_t row0;       // global row of lane 0
     int64_t M;          // rows of the problem (rows >= M are masked)
     uint32_t cvec;      // shared-memory address of the CTA's per-column vector (bias), zero padded to 256 entries
+    // derived once per warp / tile (init()): everything the hot paths need without integer arithmetic per element
+    uint32_t own[4];    // slot offsets of the 16-byte pieces 0..3 of this lane's own row (row-major side of the transpose)
+    uint32_t trn;       // slot offset of piece lane&3 of row lane/4 (global side); rows +8 are 512 bytes further
+    int rows_left;      // M - row0, clamped to [0, 32]
+    mutable uint32_t flip;   // bf16 stagings alternate between the two 2 KB halves of the slot: one __syncwarp each
+
+    __device__ __forceinline__ void init() {
+        const int x = (lane >> 1) & 3, r = lane >> 2, pc = lane & 3;
+#pragma unroll
+        for (int p2 = 0; p2 < 4; ++p2) own[p2] = (uint32_t)(lane * 64 + ((p2 ^ x) << 4));
+        trn = (uint32_t)(r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
+        flip = 0u;
+        retile(row0);
+    }
+    __device__ __forceinline__ void retile(int64_t new_row0) {
+        row0 = new_row0;
+        const int64_t left = M - row0;
+        rows_left = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+    }
 
     // b[j] = column vector entry n0 + j: 8 broadcast 16-byte shared loads (every lane reads the same address)
     __device__ __forceinline__ void colvec(int n0, float b[32]) const {
@@ -182,42 +201,41 @@ struct WarpIO {
     }
 
     __device__ __forceinline__ int64_t row() const { return row0 + lane; }
-    __device__ __forceinline__ bool valid() const { return row0 + lane < M; }
-
-    // bf16 block: row r = 64 B = 4 pieces of 16 B; piece p of row r lives at r*64 + ((p ^ ((r >> 1) & 3)) * 16)
-    static __device__ __forceinline__ uint32_t off16(int r, int p) { return (uint32_t)(r * 64 + ((p ^ ((r >> 1) & 3)) << 4)); }
+    __device__ __forceinline__ bool valid() const { return lane < rows_left; }
 
     // Coalesced read of the 32 x 32 bf16 block P[row0.., n0..n0+31] in two steps so that the global latency can be
-    // hidden: prefetch() issues the loads (lane t fetches 16-byte piece t&3 of rows i*8 + t/4), unstage() transposes
-    // them through the slot so that out[j] = P[row(), n0 + j] (rows >= M read as 0).
-    // Requires 16-byte aligned P + n0 and ld % 8 == 0.
+    // hidden: prefetch() issues the loads (lane t fetches 16-byte piece t&3 of rows i*8 + t/4; predicated, rows >= M
+    // are left undefined and must not be stored), unstage() transposes them through the slot so that
+    // out[j] = P[row(), n0 + j].  Requires 16-byte aligned P + n0 and ld % 8 == 0.
     __device__ __forceinline__ void prefetch(const __nv_bfloat16* P, int64_t ld, int n0, uint4 q[4]) const {
+        const char* base = reinterpret_cast<const char*>(P + (row0 + (lane >> 2)) * ld + n0 + (lane & 3) * 8);
+        const int64_t step = ld * 16;            // 8 rows, in bytes
+        const int r = lane >> 2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + (lane >> 2), p = lane & 3;
-            const int64_t gr = row0 + r;
-            q[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (gr < M) q[i] = __ldg(reinterpret_cast<const uint4*>(P + gr * ld + n0 + p * 8));
+            const uint32_t on = (i * 8 + r) < rows_left ? 1u : 0u;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
+                         : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w)
+                         : "l"(base + i * step), "r"(on));
         }
     }
     __device__ __forceinline__ void unstage(const uint4 q[4], float out[32]) const {
+        const uint32_t h = slot + flip;
+        flip ^= 2048u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + (lane >> 2), p = lane & 3;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + off16(r, p)), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
-        }
+        for (int i = 0; i < 4; ++i)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
         __syncwarp();
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             uint32_t w[4];
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(slot + off16(lane, p)) : "memory");
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(h + own[p]) : "memory");
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 out[p * 8 + 2 * j] = __uint_as_float(w[j] << 16);
                 out[p * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
             }
         }
-        __syncwarp();
     }
     __device__ __forceinline__ void load(const __nv_bfloat16* P, int64_t ld, int n0, float out[32]) const {
         uint4 q[4];
@@ -227,41 +245,58 @@ struct WarpIO {
 
     // P[row(), n0 + j] = v[j] for j < nvalid (<= 32); rows >= M are skipped
     __device__ __forceinline__ void store(__nv_bfloat16* P, int64_t ld, int n0, const float v[32], int nvalid) const {
+        const uint32_t h = slot + flip;
+        flip ^= 2048u;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             uint32_t w[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 h = __floats2bfloat162_rn(v[p * 8 + 2 * j], v[p * 8 + 2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&h);
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[p * 8 + 2 * j], v[p * 8 + 2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&hh);
             }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(slot + off16(lane, p)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + own[p]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
         }
         __syncwarp();
+        char* base = reinterpret_cast<char*>(P + (row0 + (lane >> 2)) * ld + n0 + (lane & 3) * 8);
+        const int64_t step = ld * 16;
+        const int r = lane >> 2;
+        const int pv = nvalid - (lane & 3) * 8;      // valid columns of this lane's piece
+        if (nvalid == 32) {
 #pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 q;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(h + trn + (uint32_t)i * 512u) : "memory");
+                const uint32_t on = (i * 8 + r) < rows_left ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+                             ::"l"(base + i * step), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w), "r"(on) : "memory");
+            }
+        } else {
+            store_ragged(h + trn, base, step, r, rows_left, pv);
+        }
+    }
+    // ragged last chunk of a layer (e.g. the 217-column layer before the skip concat): compact and out of line
+    static __device__ __noinline__ void store_ragged(uint32_t src, char* base, int64_t step, int r, int rows_left, int pv) {
+#pragma unroll 1
         for (int i = 0; i < 4; ++i) {
-            const int r = i * 8 + (lane >> 2), p = lane & 3;
-            const int64_t gr = row0 + r;
             uint4 q;
-            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(slot + off16(r, p)) : "memory");
-            if (gr < M) {
-                __nv_bfloat16* dst = P + gr * ld + n0 + p * 8;
-                if (p * 8 + 8 <= nvalid) {
-                    *reinterpret_cast<uint4*>(dst) = q;
-                } else if (p * 8 < nvalid) {   // the piece straddles the last valid column
-                    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-                    for (int j = 0; j < nvalid - p * 8; ++j) {
-                        const uint16_t h = (uint16_t)((j & 1) ? (w[j >> 1] >> 16) : (w[j >> 1] & 0xffffu));
-                        *reinterpret_cast<uint16_t*>(dst + j) = h;
-                    }
-                }
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(src + (uint32_t)i * 512u) : "memory");
+            if ((i * 8 + r) >= rows_left || pv <= 0) continue;
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base + i * step);
+            if (pv >= 8) { *reinterpret_cast<uint4*>(dst) = q; continue; }
+            uint32_t w = q.x;
+#pragma unroll 1
+            for (int j = 0; j < pv; ++j) {
+                if (j == 2) w = q.y; else if (j == 4) w = q.z; else if (j == 6) w = q.w;
+                *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu));
             }
         }
-        __syncwarp();
     }
 
     // fp32 block [32][32]: element (r, c) at r*128 + ((c ^ r) & 31)*4  (row-wise and column-wise conflict free)
     __device__ __forceinline__ void stage_f32(const float v[32]) const {
+        __syncwarp();          // the bf16 stagings do not end with a barrier; this one uses the whole slot
+        flip = 0u;
 #pragma unroll
         for (int c = 0; c < 32; ++c)
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (uint32_t)(lane * 128 + (((c ^ lane) & 31) << 2))), "f"(v[c]) : "memory");
@@ -288,15 +323,28 @@ struct WarpIO {
         __syncwarp();
     }
 
-    // C[row, c0 + j] = (C[row, c0 + j] +) v[j] for jlo <= j < jhi and rows < M: fp32, one contiguous row per request
+    // C[row, c0 + j] = (C[row, c0 + j] +) v[j] for jlo <= j < jhi and rows < M: fp32, one contiguous row per request.
+    // Rare path (first layer / skip columns): kept out of line so that it does not bloat the unrolled chunk loop.
     __device__ __forceinline__ void store_f32(float* C, int64_t ldc, int c0, const float v[32], int jlo, int jhi, bool accum) const {
-        stage_f32(v);
+        float tmp[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tmp[j] = v[j];
+        warp_store_f32(slot, lane, row0, rows_left, C, ldc, c0, tmp, jlo, jhi, accum);
+        flip = 0u;
+    }
+    static __device__ __noinline__ void warp_store_f32(uint32_t slot, int lane, int64_t row0, int rows_left, float* C, int64_t ldc,
+                                                       int c0, const float* v, int jlo, int jhi, bool accum) {
+        __syncwarp();
+#pragma unroll 4
+        for (int c = 0; c < 32; ++c)
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (uint32_t)(lane * 128 + (((c ^ lane) & 31) << 2))), "f"(v[c]) : "memory");
+        __syncwarp();
         const bool on = lane >= jlo && lane < jhi;
-        for (int r = 0; r < 32; ++r) {
-            const int64_t gr = row0 + r;
-            if (gr >= M) break;
-            const float x = staged(r);
-            if (on) { float* p = C + gr * ldc + c0 + lane; *p = accum ? *p + x : x; }
+#pragma unroll 1
+        for (int r = 0; r < rows_left; ++r) {
+            float x;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(slot + (uint32_t)(r * 128 + (((lane ^ r) & 31) << 2))) : "memory");
+            if (on) { float* p = C + (row0 + r) * ldc + c0 + lane; *p = accum ? *p + x : x; }
         }
         __syncwarp();
     }
@@ -415,10 +463,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int chunks = (BN + 31) / 32;
         uint32_t it = 0;
-        uint4 pre[Epi::kPre == 1 ? 4 : (Epi::kPre == 2 ? 2 : 1)][pre_regs<Epi>()];
+        uint4 pre[2][pre_regs<Epi>()];
+        WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)blockIdx.x * BM + q * 32, M, sV};
+        io.init();
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
-            const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, tile * BM + q * 32, M, sV};
+            io.retile(tile * BM + q * 32);
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u;
             if (Epi::kPre == 0) {
                 mbar_wait(smem_u32(&bars->tfull[a]), aph);
@@ -442,29 +492,32 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 // Rolling prefetch of the epilogue's bf16 operands, kDepth chunks ahead (across tile boundaries): the
                 // registers of a consumed chunk are refilled at once with the loads of chunk + kDepth, so global latency
                 // is covered by the math / stores of the chunks in between and never by an idle warp.
-                constexpr int kDepth = Epi::kPre == 1 ? 4 : 2;
+                constexpr int kDepth = 2;
                 if (it == 0) {
 #pragma unroll
                     for (int i = 0; i < kDepth; ++i)
                         if (half + 2 * i < chunks) epi.prefetch(io, (half + 2 * i) * 32, pre[i]);
                 }
                 const bool has_next = tile + gridDim.x < num_tiles;
-                const WarpIO io_next{io.slot, lane, (tile + gridDim.x) * BM + q * 32, M, sV};
+                WarpIO io_next = io;
+                io_next.retile((tile + gridDim.x) * BM + q * 32);
                 mbar_wait(smem_u32(&bars->tfull[a]), aph);
                 tc_fence_after();
+#pragma unroll 1
+                for (int ii = 0; ii < kMaxChunksPerWarp / kDepth; ++ii) {      // compact code: two 2-chunk bodies
 #pragma unroll
-                for (int i = 0; i < kMaxChunksPerWarp; ++i) {
-                    const int c = half + 2 * i;
-                    if (c < chunks) {
-                        float v[32];
-                        tmem_ld32(tacc + (uint32_t)c * 32u, v);
-                        epi.chunk(io, c * 32, v, pre[i % kDepth]);
-                    }
-                    const int jn = i + kDepth;                 // chunk slot that reuses these registers
-                    if (jn < kMaxChunksPerWarp) {
-                        if (half + 2 * jn < chunks) epi.prefetch(io, (half + 2 * jn) * 32, pre[i % kDepth]);
-                    } else if (has_next && half + 2 * (jn - kMaxChunksPerWarp) < chunks) {
-                        epi.prefetch(io_next, (half + 2 * (jn - kMaxChunksPerWarp)) * 32, pre[i % kDepth]);
+                    for (int k = 0; k < kDepth; ++k) {
+                        const int c = half + 2 * (ii * kDepth + k);
+                        if (c < chunks) {
+                            float v[32];
+                            tmem_ld32(tacc + (uint32_t)c * 32u, v);
+                            epi.chunk(io, c * 32, v, pre[k]);
+                        }
+                        if (ii == 0) {                                          // refill: chunk + kDepth of this tile ...
+                            if (c + 2 * kDepth < chunks) epi.prefetch(io, (c + 2 * kDepth) * 32, pre[k]);
+                        } else if (has_next && c - 2 * kDepth < chunks) {       // ... or the matching chunk of the next tile
+                            epi.prefetch(io_next, (c - 2 * kDepth) * 32, pre[k]);
+                        }
                     }
                 }
             }
@@ -554,7 +607,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         const int chunks = (BJ + 31) / 32;
         mbar_wait(smem_u32(&bars->tfull[0]), 0);
         tc_fence_after();
-        const WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)i0 + q * 32, (int64_t)1 << 40, 0u};
+        WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)i0 + q * 32, (int64_t)1 << 40, 0u};
+        io.init();
         for (int c = half; c < chunks; c += 2) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 32u, v);
