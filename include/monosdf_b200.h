@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define MSDF_MAX_LAYERS 12
-#define MSDF_ABI_VERSION 1
+#define MSDF_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ library ------------------------------ */
 const char* msdf_last_error(void);
@@ -145,13 +145,18 @@ size_t msdf_field_workspace_bytes(const msdf_mlp_desc* sdf_net, const msdf_encod
  *   d sdf / d x, replacing torch.autograd.grad(create_graph=True) (NULL in SDF_ONLY mode); feat [M, F] with
  *   leading dimension ld_feat (NULL to skip); rgb [M,3] (NULL when color_net == NULL);
  *   view_dirs [n_rays,3], point m belongs to ray m / n_samples; code [n_rays|1, code_dim] or NULL.
- * No state is kept: the backward recomputes the chunk's activations (activation memory of the reference's
- * double backward is ~0.9 MB per ray). */
+ * The library keeps no state.  With saved == NULL the backward recomputes the chunk's activations; with a caller
+ * buffer of msdf_field_saved_bytes() bytes passed to BOTH calls (MODE_FORWARD with a grad output), the forward leaves
+ * every layer's activations of both sweeps there (~10 KB per point in bf16 mode: B200's 180 GB of HBM hold a 65536-ray
+ * step) and the backward reads them back -- and overwrites them: one backward per saved forward. */
+size_t msdf_field_saved_bytes(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
+                              const msdf_color_desc* cd, int64_t M, int n_samples, unsigned flags);
+
 int msdf_field_forward(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
                        const msdf_color_desc* cd, const float* x, int64_t M, const float* view_dirs, int64_t n_rays,
                        int n_samples, const float* code, int mode, float clamp_radius, float sphere_scale,
                        unsigned flags, void* workspace, size_t workspace_bytes, float* sdf, float* grad,
-                       float* feat, int64_t ld_feat, float* rgb, void* stream);
+                       float* feat, int64_t ld_feat, float* rgb, void* saved, size_t saved_bytes, void* stream);
 
 /* Backward of the above INCLUDING the double-backward terms through grad (what loss.backward() does through
  * autograd.grad(create_graph=True) in the reference): given dL/dsdf [M], dL/dgrad [M,3], dL/dfeat [M,F] (ld),
@@ -163,7 +168,7 @@ int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* 
                         void* workspace, size_t workspace_bytes, const float* d_sdf, const float* d_grad,
                         const float* d_feat, int64_t ld_dfeat, const float* rgb, const float* d_rgb,
                         const msdf_mlp_grads* sdf_grads, const msdf_mlp_grads* color_grads, float* grad_table,
-                        float* d_code, void* stream);
+                        float* d_code, void* saved, size_t saved_bytes, void* stream);
 
 /* points[r*n + j] = o[r] + z[r,j] * d[r]   (network.py:532-533, ray_sampler.py:129) */
 int msdf_ray_points(const float* ray_o, const float* ray_d, const float* z, int64_t n_rays, int n, float* points,

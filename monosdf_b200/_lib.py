@@ -51,10 +51,11 @@ _SIGNATURES = {
     "msdf_hash_encode_second_backward": (c_int, [_P, _P, _P, _P, c_uint32, c_uint32, c_uint32, c_uint32, c_float, c_uint32, c_int, _P, _P, _P, _P, _P]),
     "msdf_field_workspace_bytes": (c_size_t, [POINTER(MlpDesc), POINTER(EncodingDesc), POINTER(MlpDesc), POINTER(ColorDesc), c_int64, c_int, c_uint]),
     "msdf_field_forward": (c_int, [POINTER(MlpDesc), POINTER(EncodingDesc), POINTER(MlpDesc), POINTER(ColorDesc), _P, c_int64, _P, c_int64,
-                                   c_int, _P, c_int, c_float, c_float, c_uint, _P, c_size_t, _P, _P, _P, c_int64, _P, _P]),
+                                   c_int, _P, c_int, c_float, c_float, c_uint, _P, c_size_t, _P, _P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "msdf_field_saved_bytes": (c_size_t, [POINTER(MlpDesc), POINTER(EncodingDesc), POINTER(MlpDesc), POINTER(ColorDesc), c_int64, c_int, c_uint]),
     "msdf_field_backward": (c_int, [POINTER(MlpDesc), POINTER(EncodingDesc), POINTER(MlpDesc), POINTER(ColorDesc), _P, c_int64, _P, c_int64,
                                     c_int, _P, c_float, c_float, c_uint, _P, c_size_t, _P, _P, _P, c_int64, _P, _P,
-                                    POINTER(MlpGrads), POINTER(MlpGrads), _P, _P, _P]),
+                                    POINTER(MlpGrads), POINTER(MlpGrads), _P, _P, _P, c_size_t, _P]),
     "msdf_ray_points": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "msdf_camera_rays": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P]),
     "msdf_render_forward": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
@@ -87,7 +88,7 @@ def lib():
             fn = getattr(h, name)   # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if h.msdf_abi_version() != 1:
+        if h.msdf_abi_version() != 2:
             raise RuntimeError("monosdf_b200: ABI version mismatch")
         _lib = h
     return _lib

@@ -203,6 +203,129 @@ __global__ void k_encode(const float* __restrict__ x, int64_t M, int pe_w, int g
     stf(H0 + m * ld0 + j, v);
 }
 
+// ---- row-per-thread producers of the padded operand rows (one thread computes a whole row and writes it in
+// 8-column vectors; the per-column form above costs one thread, one set of loads and one sin/cos call per element)
+
+// PE of a 3-vector: out[0..2] = x, then per frequency k: sin(2^k x) (3), cos(2^k x) (3).  sincosf keeps fp32 parity.
+__device__ __forceinline__ void pe_row(const float p[3], int multires, float* out) {
+    out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+    for (int k = 0; k < multires; ++k) {
+        const float f = (float)(1 << k);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) sincosf(p[d] * f, &out[3 + 6 * k + d], &out[3 + 6 * k + 3 + d]);
+    }
+}
+
+constexpr int kMaxPe = 3 + 6 * 16;
+
+// H0[m, 0:cols) = [PE(x_m) | hash features or zeros | zero padding]
+template <class T>
+__global__ void __launch_bounds__(128)
+k_encode_rows(const float* __restrict__ x, int64_t M, int multires, int pe_w, int grid_w, const float* __restrict__ hashf,
+              T* __restrict__ H0, int64_t ld0, int cols) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float p[3] = {x[3 * m], x[3 * m + 1], x[3 * m + 2]};
+    float pe[kMaxPe];
+    pe_row(p, multires, pe);
+    T* row = H0 + m * ld0;
+    for (int j0 = 0; j0 < cols; j0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            v[u] = j < pe_w ? pe[j] : ((j < pe_w + grid_w && hashf != nullptr) ? hashf[m * grid_w + (j - pe_w)] : 0.f);
+        }
+        store_row<8>(row + j0, v, cols - j0 < 8 ? cols - j0 : 8);
+    }
+}
+
+// The non-feature columns of the colour-net input row (see k_color_input), written as whole 8-column groups: only
+// used when those columns form one aligned, contiguous range [c_lo, c_hi) of the (rotated) row, i.e. bf16 mode.
+template <class T>
+__global__ void __launch_bounds__(128)
+k_color_input_rows(const float* __restrict__ x, const float* __restrict__ view, const float* __restrict__ normal,
+                   const float* __restrict__ code, int64_t M, int n_samples, int mode_idr, int multires_view, int pe_w, int cd,
+                   int code_per_ray, T* __restrict__ X, int64_t ldx, int c_lo, int c_hi) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const int64_t ray = m / n_samples;
+    const float d[3] = {view[3 * ray], view[3 * ray + 1], view[3 * ray + 2]};
+    float pe[kMaxPe];
+    pe_row(d, multires_view, pe);
+    // rotated order of the range: [code (cd) | x (3, idr) | PE(view) (pe_w) | normal (3, idr) | zero padding]
+    const int o_x = cd, o_pe = o_x + (mode_idr ? 3 : 0), o_n = o_pe + pe_w, o_end = o_n + (mode_idr ? 3 : 0);
+    T* row = X + m * ldx + c_lo;
+    for (int j0 = 0; j0 < c_hi - c_lo; j0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            float t = 0.f;
+            if (j < o_x) t = code[(code_per_ray ? ray : 0) * cd + j];
+            else if (j < o_pe) t = x[3 * m + (j - o_x)];
+            else if (j < o_n) t = pe[j - o_pe];
+            else if (j < o_end) t = normal[3 * m + (j - o_n)];
+            v[u] = t;
+        }
+        store_row<8>(row + j0, v, 8);
+    }
+}
+
+// Backward prologue, row part: dn[m] = mask (d_grad + dn_color); TG0[m, :] = J_enc dn (zero padded); and the columns
+// [tail_lo, out_cols) of Dout: the sdf adjoint at sdf_col, zeros elsewhere (the feature columns are handled by
+// k_backward_prologue only when they need work).
+template <class T>
+__global__ void __launch_bounds__(128)
+k_backward_rows(const float* __restrict__ x, int64_t M, int multires, int pe_w, int grid_w, int n_levels, int level_dim,
+                const float* __restrict__ dy_dx, float hash_chain, const float* __restrict__ mask,
+                const float* __restrict__ d_sdf, const float* __restrict__ d_grad, const float* __restrict__ dn_color,
+                int sdf_col, int tail_lo, T* __restrict__ Dout, int64_t ldo, int out_cols, float* __restrict__ dn,
+                T* __restrict__ TG0, int64_t ldt, int t_cols) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const float mk = mask[m];
+    float v[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) v[d] = mk * ((d_grad ? d_grad[3 * m + d] : 0.f) + (dn_color ? dn_color[3 * m + d] : 0.f));
+    dn[3 * m] = v[0]; dn[3 * m + 1] = v[1]; dn[3 * m + 2] = v[2];
+    const float p[3] = {x[3 * m], x[3 * m + 1], x[3 * m + 2]};
+    float pe[kMaxPe];
+    pe_row(p, multires, pe);            // d/dx sin(f x) = f cos(f x), d/dx cos(f x) = -f sin(f x)
+    T* trow = TG0 + m * ldt;
+    const int d0 = pe_w + grid_w;
+    for (int j0 = 0; j0 < t_cols; j0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            float r = 0.f;
+            if (j < 3) r = v[j];
+            else if (j < pe_w) {
+                const int k = (j - 3) / 6, q = (j - 3) - 6 * k;
+                const float f = (float)(1 << k);
+                r = q < 3 ? f * pe[j + 3] * v[q] : -f * pe[j - 3] * v[q - 3];
+            } else if (j < d0 && dy_dx != nullptr) {
+                const int qq = j - pe_w, l = qq / level_dim, c = qq - l * level_dim;
+                const float* dd = dy_dx + m * (int64_t)(n_levels * 3 * level_dim) + (l * 3) * level_dim + c;
+                r = (dd[0] * v[0] + dd[level_dim] * v[1] + dd[2 * level_dim] * v[2]) * hash_chain;
+            }
+            t[u] = r;
+        }
+        store_row<8>(trow + j0, t, t_cols - j0 < 8 ? t_cols - j0 : 8);
+    }
+    if (tail_lo >= 0) {
+        T* drow = Dout + m * ldo;
+        const float ds = d_sdf ? mk * d_sdf[m] : 0.f;
+        for (int j0 = tail_lo; j0 < out_cols; j0 += 8) {
+            float t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) t[u] = (j0 + u == sdf_col) ? ds : 0.f;
+            store_row<8>(drow + j0, t, out_cols - j0 < 8 ? out_cols - j0 : 8);
+        }
+    }
+}
+
 template <class T>
 __global__ void k_zero_cols(T* __restrict__ dst, int64_t ld, int64_t M, int c0, int w) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -730,17 +853,53 @@ struct EpiColorIn : EpiBase<EpiColorIn<T>> {
         }
     }
 };
+// colour head on the tensor cores (bf16 mode): out[m, n] = act(acc + b[n]), n < N <= 4, fp32 output
+struct EpiHead : EpiBase<EpiHead> {
+    const float* bias; float* out; int64_t ldo; int act;
+    template <int W> __device__ __forceinline__ void run(int64_t, int, const float*, int) const {}
+    __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4*) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+        float b[32];
+        io.colvec(n0, b);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float p = v[j] + b[j];
+            v[j] = act == kActSigmoid ? 1.0f / (1.0f + __expf(-p)) : (act == kActRelu ? fmaxf(p, 0.f) : p);
+        }
+        io.store_f32(out, ldo, n0, v, 0, nv, false);
+    }
+    __device__ __forceinline__ const float* colvec() const { return bias; }
+};
+
+// dpre[m, n] = d_out[m, n] * act'(out[m, n]) for n < N, zero padded to `cols` columns (operand of the head's
+// dgrad / wgrad GEMMs in bf16 mode)
+template <class T>
+__global__ void __launch_bounds__(128)
+k_head_dpre(const float* __restrict__ d_out, const float* __restrict__ out, int64_t M, int N, int act, T* __restrict__ D, int64_t ldd, int cols) {
+    const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    T* row = D + m * ldd;
+    for (int j0 = 0; j0 < cols; j0 += 8) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) t[u] = (j0 + u < N) ? d_out[m * N + j0 + u] * act_grad(act, out[m * N + j0 + u]) : 0.f;
+        store_row<8>(row + j0, t, cols - j0 < 8 ? cols - j0 : 8);
+    }
+}
+
 // reverse-sweep start: a_{L-1} = e_0, so (a W_{L-1})[m,n] = W_{L-1}[0,n] for every point
 template <class T>
 __global__ void k_rev_init(const float* __restrict__ w_row, int64_t M, int N, EpiRev<T> epi) {
+    constexpr int G = kIsBf16<T> ? 8 : 4;          // columns per thread: one 16-byte vector of T
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int n4 = (N + 3) / 4;
-    if (i >= M * n4) return;
-    const int64_t m = i / n4; const int n = (int)(i - m * n4) * 4;
-    float v[4];
+    const int ng = (N + G - 1) / G;
+    if (i >= M * ng) return;
+    const int64_t m = i / ng; const int n = (int)(i - m * ng) * G;
+    float v[G];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (n + j < N) ? __ldg(w_row + n + j) : 0.f;
-    epi.template run<4>(m, n, v, (N - n) < 4 ? (N - n) : 4);
+    for (int j = 0; j < G; ++j) v[j] = (n + j < N) ? __ldg(w_row + n + j) : 0.f;
+    epi.template run<G>(m, n, v, (N - n) < G ? (N - n) : G);
 }
 
 // colour-net input row (network.py:393-413): idr [x, PE(view), normal, feat, code], nerf [PE(view), feat, code].
@@ -839,7 +998,7 @@ struct Bufs {
     T* A[MSDF_MAX_LAYERS];   // a_l, later z_l / pbar_l  (l < L-1)
     T *TG0, *T2[2], *Dout;
     float *G0, *BH0, *dydx, *hashf, *sdf_raw, *mask, *dn, *dn_color, *gradc, *sdfc, *dcode;
-    T* X; T* C[MSDF_MAX_LAYERS]; T* dC[2];
+    T* X; T* C[MSDF_MAX_LAYERS]; T* dC[2]; T* Hd;   // Hd: colour head dpre, [Mc, 64] (bf16 mode)
     int64_t d0p, ldh, ldo, ldx, ldc;   // leading dimensions
 };
 
@@ -861,11 +1020,17 @@ struct Ctx {
 };
 
 // mode: MSDF_MODE_*.  sn_w / cn_w (may be null) receive the bf16 weight-copy pointers.
+// With split == true the activations the backward needs (the "persistent" group: H, A, G0, dy_dx, mask, colour-net
+// rows) are carved from `saved` instead of the workspace and *saved_size receives their size: the forward of a
+// training step writes them there and the backward reads them back instead of recomputing the chunk.
 template <class T>
-size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* sn_w, Net* cn_w) {
+size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* sn_w, Net* cn_w, void* saved = nullptr,
+             bool split = false, size_t* saved_size = nullptr) {
     const Net& sn = cx.sn;
     const msdf_encoding_desc* enc = cx.enc;
     Carver c{(char*)ws, 0, ws == nullptr};
+    Carver ps{(char*)saved, 0, saved == nullptr};
+    Carver& p = split ? ps : c;
     Bufs<T> b{};
     if (kIsBf16<T>) {   // weight copies first (fixed size, independent of the chunk)
         Net* dst[2] = {sn_w, cn_w};
@@ -879,23 +1044,23 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
     }
     const bool grid_feats = enc->grid_feat_dim > 0 && enc->table != nullptr;
     b.d0p = padw<T>(sn.d0); b.ldh = padw<T>(sn.maxw);
-    b.H[0] = c.take<T>(Mc, b.d0p);
+    b.H[0] = p.take<T>(Mc, b.d0p);
     b.sdf_raw = c.take<float>(Mc, 1);
     if (grid_feats && kIsBf16<T>) b.hashf = c.take<float>(Mc, enc->grid_feat_dim);
     if (mode == MSDF_MODE_SDF_ONLY) {
         T* pp[2] = {c.take<T>(Mc, b.ldh), c.take<T>(Mc, b.ldh)};
         for (int l = 1; l < sn.L; ++l) b.H[l] = pp[(l - 1) & 1];
     } else {
-        for (int l = 1; l < sn.L; ++l) b.H[l] = c.take<T>(Mc, b.ldh);
-        if (mode == MSDF_MODE_FORWARD) {
+        for (int l = 1; l < sn.L; ++l) b.H[l] = p.take<T>(Mc, b.ldh);
+        if (mode == MSDF_MODE_FORWARD && !split) {
             T* pp[2] = {c.take<T>(Mc, b.ldh), c.take<T>(Mc, b.ldh)};
             for (int l = 0; l < sn.L - 1; ++l) b.A[l] = pp[l & 1];
         } else {
-            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = c.take<T>(Mc, b.ldh);
+            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = p.take<T>(Mc, b.ldh);
         }
-        b.G0 = c.take<float>(Mc, round_up(sn.d0, 4));
-        if (grid_feats) b.dydx = c.take<float>(Mc, enc->n_levels * 3 * enc->level_dim);
-        b.mask = c.take<float>(Mc, 1);
+        b.G0 = p.take<float>(Mc, round_up(sn.d0, 4));
+        if (grid_feats) b.dydx = p.take<float>(Mc, enc->n_levels * 3 * enc->level_dim);
+        b.mask = p.take<float>(Mc, 1);
         if (mode == MSDF_MODE_BACKWARD) {
             b.TG0 = c.take<T>(Mc, b.d0p);
             if (grid_feats) b.BH0 = c.take<float>(Mc, round_up(sn.d0, 4));
@@ -907,17 +1072,34 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
         }
         if (cx.has_color) {
             b.ldx = padw<T>(cx.cg.in0); b.ldc = padw<T>(cx.cn.maxw);
-            b.X = c.take<T>(Mc, b.ldx);
+            b.X = p.take<T>(Mc, b.ldx);
             b.C[0] = b.X;
-            for (int l = 1; l < cx.cn.L; ++l) b.C[l] = c.take<T>(Mc, b.ldc);
+            for (int l = 1; l < cx.cn.L; ++l) b.C[l] = p.take<T>(Mc, b.ldc);
             if (mode == MSDF_MODE_BACKWARD) {
                 b.dC[0] = c.take<T>(Mc, b.ldc); b.dC[1] = c.take<T>(Mc, b.ldc);
+                if (kIsBf16<T>) b.Hd = c.take<T>(Mc, 64);
                 if (cx.cd->code_dim > 0) b.dcode = c.take<float>(Mc, cx.cd->code_dim);
             }
         }
     }
     if (out) *out = b;
+    if (saved_size) *saved_size = ps.off;
     return c.off;
+}
+
+// Chunking of the saved-activation mode: a function of the problem only, so that forward and backward agree.
+template <class T>
+int64_t saved_chunk(const Ctx& cx, int64_t M, int n_samples) {
+    const int64_t cap = kIsBf16<T> ? 262144 : 65536;   // the caps of pick_chunk
+    int64_t mc = M < cap ? M : cap;
+    if (cx.has_color && mc < M) mc = mc / n_samples * n_samples;
+    return mc;
+}
+template <class T>
+size_t saved_stride(const Ctx& cx, int64_t chunk) {
+    size_t sz = 0;
+    carve<T>(cx, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, nullptr, nullptr, nullptr, nullptr, nullptr, true, &sz);
+    return sz;
 }
 
 template <class T>
@@ -1023,7 +1205,7 @@ int encode_chunk(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, boo
         k_encode<T><<<nblk(Mc * c.pe_w), 256, 0, c.st>>>(x, Mc, c.pe_w, 0, nullptr, b.H[0], b.d0p, c.pe_w);
     } else {                       // PE + staged hash features (or zero features) + zero padding
         const int cols = (int)b.d0p;
-        k_encode<T><<<nblk(Mc * cols), 256, 0, c.st>>>(x, Mc, c.pe_w, gw, c.grid ? b.hashf : nullptr, b.H[0], b.d0p, cols);
+        k_encode_rows<T><<<nblk(Mc, 128), 128, 0, c.st>>>(x, Mc, c.enc->multires, c.pe_w, gw, c.grid ? b.hashf : nullptr, b.H[0], b.d0p, cols);
     }
     LAUNCHED("encode");
     return MSDF_OK;
@@ -1073,8 +1255,8 @@ int reverse_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc) {
     const Net& n = c.sn;
     {
         const int l = n.L - 1;
-        const int n4 = (n.in[l] + 3) / 4;
-        k_rev_init<T><<<nblk(Mc * n4), 256, 0, c.st>>>(n.W[l], Mc, n.in[l], make_rev<T>(n, b, l));
+        const int ng = (n.in[l] + (kIsBf16<T> ? 7 : 3)) / (kIsBf16<T> ? 8 : 4);
+        k_rev_init<T><<<nblk(Mc * ng), 256, 0, c.st>>>(n.W[l], Mc, n.in[l], make_rev<T>(n, b, l));
         LAUNCHED("reverse init");
     }
     for (int l = n.L - 2; l >= 0; --l) {
@@ -1105,8 +1287,15 @@ int color_forward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, co
     const int pad = (int)b.ldx - g.in0;
     const int cols = g.in0 - c.cd->feat_dim + pad;
     // chunks start on a ray boundary; view / code pointers are already offset to the chunk's first ray
-    k_color_input<T><<<nblk(Mc * cols), 256, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, g.pe_w, c.cd->feat_dim,
-                                                       c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, pad, n.rot0);
+    if (kIsBf16<T> && n.rot0 == g.fc && c.cd->feat_dim % 8 == 0) {
+        // rotated row: [feat | code | x | PE(view) | normal | padding]: everything after feat is one aligned range
+        k_color_input_rows<T><<<nblk(Mc, 128), 128, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, c.cd->multires_view,
+                                                              g.pe_w, c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, c.cd->feat_dim,
+                                                              (int)b.ldx);
+    } else {
+        k_color_input<T><<<nblk(Mc * cols), 256, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, g.pe_w, c.cd->feat_dim,
+                                                           c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, pad, n.rot0);
+    }
     LAUNCHED("colour input");
     for (int l = 0; l < n.L - 1; ++l) {
         EpiRelu<T> e{};
@@ -1116,6 +1305,12 @@ int color_forward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, co
     const int l = n.L - 1;
     MSDF_CHECK_ARG(n.out[l] <= 4, "colour net: d_out=%d > 4 unsupported", n.out[l]);
     if (rgb == nullptr) return MSDF_OK;   // backward recompute: the saved rgb drives act', the head is not needed
+    if constexpr (kIsBf16<T>) {
+        EpiHead e{};
+        e.bias = n.b[l]; e.out = rgb; e.ldo = n.out[l]; e.act = c.cd->final_act == 0 ? kActSigmoid : kActRelu;
+        RUN((gemm_nt<T>(c, n, l, b.C[l], b.ldc, Mc, 0, n.out[l], e, "colour head")));
+        return MSDF_OK;
+    }
     k_rowdot<4, T><<<nblk(Mc, 8), 256, 0, c.st>>>(b.C[l], b.ldc, n.W[l], n.ldw[l], n.b[l], Mc, n.out[l], n.in[l],
                                                  c.cd->final_act == 0 ? kActSigmoid : kActRelu, rgb, n.out[l]);
     LAUNCHED("colour head");
@@ -1128,13 +1323,24 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
     const ColorGeom& g = c.cg;
     int l = n.L - 1;
     const int act = c.cd->final_act == 0 ? kActSigmoid : kActRelu;
-    k_rowdot_wgrad<4, T><<<nblk(Mc, 512), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, b.C[l], b.ldc, Mc, n.out[l], n.in[l], 512,
-                                                         gr->dW[l], n.ldw[l], gr->db[l]);
-    LAUNCHED("colour head wgrad");
     T* P = b.dC[0];
-    k_rowdot_dgrad<4, T><<<nblk(Mc * n.in[l]), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, n.W[l], n.ldw[l], b.C[l], b.ldc, Mc,
-                                                              n.out[l], n.in[l], P, b.ldc);
-    LAUNCHED("colour head dgrad");
+    if constexpr (kIsBf16<T>) {
+        // the 3-wide head as zero-padded tensor-core GEMMs: dpre [Mc, 64] is the operand of its wgrad and dgrad
+        k_head_dpre<T><<<nblk(Mc, 128), 128, 0, c.st>>>(d_rgb, rgb, Mc, n.out[l], act, b.Hd, 64, 64);
+        LAUNCHED("colour head dpre");
+        RUN(wgrad<T>(c, b.Hd, 64, b.C[l], b.ldc, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+        RUN(colsum<T>(c, b.Hd, 64, nullptr, 0, Mc, n.out[l], gr->db[l]));
+        EpiBwdRelu<T> e{};
+        e.Hin = b.C[l]; e.ldh = b.ldc; e.out = P; e.ldo = b.ldc;
+        RUN((gemm_nn<T>(c, n, l, b.Hd, 64, Mc, e, "colour head dgrad")));
+    } else {
+        k_rowdot_wgrad<4, T><<<nblk(Mc, 512), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, b.C[l], b.ldc, Mc, n.out[l], n.in[l], 512,
+                                                             gr->dW[l], n.ldw[l], gr->db[l]);
+        LAUNCHED("colour head wgrad");
+        k_rowdot_dgrad<4, T><<<nblk(Mc * n.in[l]), 256, 0, c.st>>>(d_rgb, rgb, n.out[l], act, n.W[l], n.ldw[l], b.C[l], b.ldc, Mc,
+                                                                  n.out[l], n.in[l], P, b.ldc);
+        LAUNCHED("colour head dgrad");
+    }
     int pp = 0;
     for (l = n.L - 2; l >= 0; --l) {
         const int64_t ldin = l == 0 ? b.ldx : b.ldc;
@@ -1264,16 +1470,30 @@ int make_ctx(Ctx& c, const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc
 template <class T>
 int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int n_samples, const float* code, int mode,
                   void* workspace, size_t workspace_bytes, float* sdf, float* grad, float* feat, int64_t ld_feat, float* rgb,
-                  const char* who) {
-    int64_t chunk = pick_chunk<T>(c, M, mode, workspace_bytes);
-    MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
-                   carve<T>(c, 128, mode, nullptr, nullptr, nullptr, nullptr));
-    if (c.has_color && chunk < M) {   // keep chunks ray aligned
-        chunk = chunk / n_samples * n_samples;
-        MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
+                  void* saved, size_t saved_bytes, const char* who) {
+    const bool saving = saved != nullptr && mode == MSDF_MODE_FORWARD;
+    int64_t chunk;
+    size_t stride = 0;
+    if (saving) {
+        MSDF_CHECK_ARG(grad != nullptr, "%s: saving activations needs the grad output", who);
+        chunk = saved_chunk<T>(c, M, n_samples);
+        MSDF_CHECK_ARG(chunk > 0, "%s: n_samples=%d exceeds the chunk size", who, n_samples);
+        stride = saved_stride<T>(c, chunk);
+        const size_t need = stride * (size_t)((M + chunk - 1) / chunk);
+        MSDF_CHECK_ARG(saved_bytes >= need, "%s: saved buffer of %zu bytes, need %zu", who, saved_bytes, need);
+        const size_t wneed = carve<T>(c, (chunk + 127) / 128 * 128, mode, nullptr, nullptr, nullptr, nullptr, nullptr, true);
+        MSDF_CHECK_ARG(workspace_bytes >= wneed, "%s: workspace of %zu bytes, need %zu with saved activations", who, workspace_bytes, wneed);
+    } else {
+        chunk = pick_chunk<T>(c, M, mode, workspace_bytes);
+        MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
+                       carve<T>(c, 128, mode, nullptr, nullptr, nullptr, nullptr));
+        if (c.has_color && chunk < M) {   // keep chunks ray aligned
+            chunk = chunk / n_samples * n_samples;
+            MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
+        }
     }
     Bufs<T> b{};
-    carve<T>(c, (chunk + 127) / 128 * 128, mode, workspace, &b, &c.sn, &c.cn);
+    carve<T>(c, (chunk + 127) / 128 * 128, mode, workspace, &b, &c.sn, &c.cn, saved, saving);
     if (kIsBf16<T>) {
         RUN(prep_weights(c, c.sn, 1));
         if (c.has_color) { c.cn.rot0 = c.cg.fc; RUN(prep_weights(c, c.cn, 0)); }
@@ -1283,13 +1503,16 @@ int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int
     for (int64_t m0 = 0; m0 < M; m0 += chunk) {
         const int64_t Mc = (M - m0 < chunk) ? M - m0 : chunk;
         const float* xc = x + 3 * m0;
+        if (saving && m0 > 0)   // this chunk's slice of the saved buffer (the workspace part is reused)
+            carve<T>(c, (chunk + 127) / 128 * 128, mode, workspace, &b, nullptr, nullptr, (char*)saved + stride * (size_t)(m0 / chunk), true);
         RUN(encode_chunk<T>(c, b, xc, Mc, with_grad));
         T* featc = nullptr; int64_t ldf_ = 0;
         if (c.has_color) { featc = b.X + (kIsBf16<T> ? 0 : c.cg.fc); ldf_ = b.ldx; }
         else if (feat != nullptr) { featc = reinterpret_cast<T*>(feat + m0 * ld_feat); ldf_ = ld_feat; }
         RUN(forward_sweep<T>(c, b, Mc, featc, ldf_));
         if (with_grad) RUN(reverse_sweep<T>(c, b, Mc));
-        RUN(decode_chunk<T>(c, b, xc, Mc, with_grad, sdf ? sdf + m0 : nullptr, with_grad ? grad + 3 * m0 : nullptr, nullptr));
+        RUN(decode_chunk<T>(c, b, xc, Mc, with_grad, sdf ? sdf + m0 : nullptr, with_grad ? grad + 3 * m0 : nullptr,
+                            saving ? b.mask : nullptr));
         if (c.has_color) {
             const int64_t ray0 = m0 / n_samples;
             RUN(color_forward<T>(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
@@ -1304,16 +1527,29 @@ template <class T>
 int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int n_samples, const float* code, void* workspace,
                    size_t workspace_bytes, const float* d_sdf, const float* d_grad, const float* d_feat, int64_t ld_dfeat,
                    const float* rgb, const float* d_rgb, const msdf_mlp_grads* sdf_grads, const msdf_mlp_grads* color_grads,
-                   float* grad_table, float* d_code, const char* who) {
-    int64_t chunk = pick_chunk<T>(c, M, MSDF_MODE_BACKWARD, workspace_bytes);
-    MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
-                   carve<T>(c, 128, MSDF_MODE_BACKWARD, nullptr, nullptr, nullptr, nullptr));
-    if (c.has_color && chunk < M) {   // keep chunks ray aligned
-        chunk = chunk / n_samples * n_samples;
-        MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
+                   float* grad_table, float* d_code, void* saved, size_t saved_bytes, const char* who) {
+    const bool have_saved = saved != nullptr;
+    int64_t chunk;
+    size_t stride = 0;
+    if (have_saved) {
+        chunk = saved_chunk<T>(c, M, n_samples);
+        MSDF_CHECK_ARG(chunk > 0, "%s: n_samples=%d exceeds the chunk size", who, n_samples);
+        stride = saved_stride<T>(c, chunk);
+        const size_t need = stride * (size_t)((M + chunk - 1) / chunk);
+        MSDF_CHECK_ARG(saved_bytes >= need, "%s: saved buffer of %zu bytes, need %zu", who, saved_bytes, need);
+        const size_t wneed = carve<T>(c, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, nullptr, nullptr, nullptr, nullptr, nullptr, true);
+        MSDF_CHECK_ARG(workspace_bytes >= wneed, "%s: workspace of %zu bytes, need %zu with saved activations", who, workspace_bytes, wneed);
+    } else {
+        chunk = pick_chunk<T>(c, M, MSDF_MODE_BACKWARD, workspace_bytes);
+        MSDF_CHECK_ARG(chunk > 0, "%s: workspace of %zu bytes is too small (need %zu for 128 points)", who, workspace_bytes,
+                       carve<T>(c, 128, MSDF_MODE_BACKWARD, nullptr, nullptr, nullptr, nullptr));
+        if (c.has_color && chunk < M) {   // keep chunks ray aligned
+            chunk = chunk / n_samples * n_samples;
+            MSDF_CHECK_ARG(chunk > 0, "%s: workspace too small for one ray of %d samples", who, n_samples);
+        }
     }
     Bufs<T> b{};
-    carve<T>(c, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, workspace, &b, &c.sn, &c.cn);
+    carve<T>(c, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, workspace, &b, &c.sn, &c.cn, saved, have_saved);
     if (kIsBf16<T>) {
         RUN(prep_weights(c, c.sn, 1));
         if (c.has_color) { c.cn.rot0 = c.cg.fc; RUN(prep_weights(c, c.cn, 0)); }
@@ -1324,17 +1560,25 @@ int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, in
     for (int64_t m0 = 0; m0 < M; m0 += chunk) {
         const int64_t Mc = (M - m0 < chunk) ? M - m0 : chunk;
         const float* xc = x + 3 * m0;
-        // ---- recompute the chunk
-        RUN(encode_chunk<T>(c, b, xc, Mc, true));
-        RUN(forward_sweep<T>(c, b, Mc, c.has_color ? b.X + (kIsBf16<T> ? 0 : c.cg.fc) : nullptr, c.has_color ? b.ldx : 0));
-        RUN(reverse_sweep<T>(c, b, Mc));
-        RUN(decode_chunk<T>(c, b, xc, Mc, true, b.sdfc, b.gradc, b.mask));
+        if (have_saved) {
+            // ---- the forward of this step left the chunk's activations in `saved`
+            if (m0 > 0)
+                carve<T>(c, (chunk + 127) / 128 * 128, MSDF_MODE_BACKWARD, workspace, &b, nullptr, nullptr,
+                         (char*)saved + stride * (size_t)(m0 / chunk), true);
+        } else {
+            // ---- recompute the chunk
+            RUN(encode_chunk<T>(c, b, xc, Mc, true));
+            RUN(forward_sweep<T>(c, b, Mc, c.has_color ? b.X + (kIsBf16<T> ? 0 : c.cg.fc) : nullptr, c.has_color ? b.ldx : 0));
+            RUN(reverse_sweep<T>(c, b, Mc));
+            RUN(decode_chunk<T>(c, b, xc, Mc, true, b.sdfc, b.gradc, b.mask));
+        }
         if (c.has_color) {
             const int64_t ray0 = m0 / n_samples;
             const int no = c.cn.out[c.cn.L - 1];
             const msdf_color_desc* cd = c.cd;
-            RUN(color_forward<T>(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
-                                 code ? code + (cd->code_per_ray ? ray0 * cd->code_dim : 0) : nullptr, b.gradc, nullptr));
+            if (!have_saved)
+                RUN(color_forward<T>(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
+                                     code ? code + (cd->code_per_ray ? ray0 * cd->code_dim : 0) : nullptr, b.gradc, nullptr));
             RUN(color_backward<T>(c, b, Mc, rgb + (int64_t)no * m0, d_rgb + (int64_t)no * m0, color_grads));
             if (cd->code_dim > 0 && d_code) {
                 if (cd->code_per_ray) {
@@ -1349,12 +1593,21 @@ int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, in
         // ---- adjoints of (sdf, feat, grad) -> tangent of the encoded input
         {
             const int t_cols = (int)b.d0p, out_cols = (int)b.ldo;
-            const int cols = t_cols > out_cols ? t_cols : out_cols;
-            k_backward_prologue<T><<<nblk(Mc * cols), 256, 0, c.st>>>(
-                xc, Mc, c.pe_w, c.enc->grid_feat_dim, c.enc->n_levels, c.enc->level_dim, c.grid ? b.dydx : nullptr, c.hash_chain,
-                b.mask, d_sdf ? d_sdf + m0 : nullptr, d_grad ? d_grad + 3 * m0 : nullptr, c.has_color ? b.dn_color : nullptr,
-                d_feat ? d_feat + m0 * ld_dfeat : nullptr, ld_dfeat, feat_w, c.has_color ? 1 : 0, sdf_col, feat_col0, b.Dout, b.ldo,
-                out_cols, b.dn, b.TG0, b.d0p, t_cols);
+            // bf16 layout [features..., sdf, padding] with the features already written by the colour dgrad and no
+            // external d_feat: only the tail columns need writing, done by the row kernel
+            const bool tail_only = kIsBf16<T> && c.has_color && d_feat == nullptr && feat_w % 8 == 0;
+            if (!tail_only) {
+                k_backward_prologue<T><<<nblk(Mc * out_cols), 256, 0, c.st>>>(
+                    xc, Mc, c.pe_w, c.enc->grid_feat_dim, c.enc->n_levels, c.enc->level_dim, c.grid ? b.dydx : nullptr, c.hash_chain,
+                    b.mask, d_sdf ? d_sdf + m0 : nullptr, d_grad ? d_grad + 3 * m0 : nullptr, c.has_color ? b.dn_color : nullptr,
+                    d_feat ? d_feat + m0 * ld_dfeat : nullptr, ld_dfeat, feat_w, c.has_color ? 1 : 0, sdf_col, feat_col0, b.Dout, b.ldo,
+                    out_cols, b.dn, b.TG0, b.d0p, 0);
+                LAUNCHED("backward prologue (output adjoints)");
+            }
+            k_backward_rows<T><<<nblk(Mc, 128), 128, 0, c.st>>>(
+                xc, Mc, c.enc->multires, c.pe_w, c.enc->grid_feat_dim, c.enc->n_levels, c.enc->level_dim, c.grid ? b.dydx : nullptr,
+                c.hash_chain, b.mask, d_sdf ? d_sdf + m0 : nullptr, d_grad ? d_grad + 3 * m0 : nullptr,
+                c.has_color ? b.dn_color : nullptr, sdf_col, tail_only ? feat_w : -1, b.Dout, b.ldo, out_cols, b.dn, b.TG0, b.d0p, t_cols);
             LAUNCHED("backward prologue");
         }
         RUN(sdf_backward<T>(c, b, xc, Mc, sdf_grads, grad_table));
@@ -1384,11 +1637,29 @@ extern "C" size_t msdf_field_workspace_bytes(const msdf_mlp_desc* sdf_net, const
     return carve<float>(c, mc, mode, nullptr, nullptr, nullptr, nullptr);
 }
 
+extern "C" size_t msdf_field_saved_bytes(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
+                                         const msdf_color_desc* cd, int64_t M, int n_samples, unsigned flags) {
+    Ctx c{};
+    msdf_mlp_desc tmp_s = *sdf_net;
+    static const float dummy = 0.f;
+    for (int l = 0; l < tmp_s.n_layers && l < MSDF_MAX_LAYERS; ++l) { if (!tmp_s.W[l]) tmp_s.W[l] = &dummy; if (!tmp_s.b[l]) tmp_s.b[l] = &dummy; }
+    msdf_mlp_desc tmp_c{};
+    if (color_net) { tmp_c = *color_net; for (int l = 0; l < tmp_c.n_layers && l < MSDF_MAX_LAYERS; ++l) { if (!tmp_c.W[l]) tmp_c.W[l] = &dummy; if (!tmp_c.b[l]) tmp_c.b[l] = &dummy; } }
+    if (make_ctx(c, &tmp_s, enc, color_net ? &tmp_c : nullptr, cd, 0.f, 1.f, nullptr, flags, "msdf_field_saved_bytes")) return 0;
+    if (M <= 0) return 0;
+    if (n_samples < 1) n_samples = 1;
+    const bool tc = (flags & MSDF_FLAG_TENSOR_BF16) != 0;
+    const int64_t chunk = tc ? saved_chunk<bf16>(c, M, n_samples) : saved_chunk<float>(c, M, n_samples);
+    if (chunk <= 0) return 0;
+    const size_t stride = tc ? saved_stride<bf16>(c, chunk) : saved_stride<float>(c, chunk);
+    return stride * (size_t)((M + chunk - 1) / chunk);
+}
+
 extern "C" int msdf_field_forward(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
                                   const msdf_color_desc* cd, const float* x, int64_t M, const float* view_dirs, int64_t n_rays,
                                   int n_samples, const float* code, int mode, float clamp_radius, float sphere_scale,
                                   unsigned flags, void* workspace, size_t workspace_bytes, float* sdf, float* grad,
-                                  float* feat, int64_t ld_feat, float* rgb, void* stream) {
+                                  float* feat, int64_t ld_feat, float* rgb, void* saved, size_t saved_bytes, void* stream) {
     const char* who = "msdf_field_forward";
     MSDF_CHECK_ARG(mode == MSDF_MODE_SDF_ONLY || mode == MSDF_MODE_FORWARD, "%s: bad mode %d", who, mode);
     if (mode == MSDF_MODE_SDF_ONLY) color_net = nullptr;
@@ -1404,8 +1675,8 @@ extern "C" int msdf_field_forward(const msdf_mlp_desc* sdf_net, const msdf_encod
         MSDF_CHECK_ARG(feat == nullptr, "%s: feat output and colour net are mutually exclusive", who);
     }
     if (flags & MSDF_FLAG_TENSOR_BF16)
-        return field_forward<bf16>(c, x, M, view_dirs, n_samples, code, mode, workspace, workspace_bytes, sdf, grad, feat, ld_feat, rgb, who);
-    return field_forward<float>(c, x, M, view_dirs, n_samples, code, mode, workspace, workspace_bytes, sdf, grad, feat, ld_feat, rgb, who);
+        return field_forward<bf16>(c, x, M, view_dirs, n_samples, code, mode, workspace, workspace_bytes, sdf, grad, feat, ld_feat, rgb, saved, saved_bytes, who);
+    return field_forward<float>(c, x, M, view_dirs, n_samples, code, mode, workspace, workspace_bytes, sdf, grad, feat, ld_feat, rgb, saved, saved_bytes, who);
 }
 
 extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc, const msdf_mlp_desc* color_net,
@@ -1414,7 +1685,7 @@ extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_enco
                                    void* workspace, size_t workspace_bytes, const float* d_sdf, const float* d_grad,
                                    const float* d_feat, int64_t ld_dfeat, const float* rgb, const float* d_rgb,
                                    const msdf_mlp_grads* sdf_grads, const msdf_mlp_grads* color_grads, float* grad_table,
-                                   float* d_code, void* stream) {
+                                   float* d_code, void* saved, size_t saved_bytes, void* stream) {
     const char* who = "msdf_field_backward";
     if (d_rgb == nullptr) color_net = nullptr;
     Ctx c{};
@@ -1429,9 +1700,9 @@ extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_enco
     }
     if (flags & MSDF_FLAG_TENSOR_BF16)
         return field_backward<bf16>(c, x, M, view_dirs, n_samples, code, workspace, workspace_bytes, d_sdf, d_grad, d_feat, ld_dfeat,
-                                    rgb, d_rgb, sdf_grads, color_grads, grad_table, d_code, who);
+                                    rgb, d_rgb, sdf_grads, color_grads, grad_table, d_code, saved, saved_bytes, who);
     return field_backward<float>(c, x, M, view_dirs, n_samples, code, workspace, workspace_bytes, d_sdf, d_grad, d_feat, ld_dfeat,
-                                 rgb, d_rgb, sdf_grads, color_grads, grad_table, d_code, who);
+                                 rgb, d_rgb, sdf_grads, color_grads, grad_table, d_code, saved, saved_bytes, who);
 }
 
 extern "C" int msdf_ray_points(const float* ray_o, const float* ray_d, const float* z, int64_t n_rays, int n, float* points,

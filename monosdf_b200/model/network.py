@@ -25,6 +25,10 @@ from .ray_sampler import ErrorBoundSampler
 
 _GB = 1 << 30
 WORKSPACE_CAP_BYTES = 6 * _GB     # per-call scratch; the library chunks the points to fit
+# Training keeps every layer's activations of a field evaluation in HBM between forward and backward (~10 KB per point
+# in bf16 mode, 64 GB for a 65536-ray step) instead of recomputing them, when they fit in this fraction of the FREE
+# device memory; set to 0 to always recompute.
+SAVED_ACTIVATION_FRACTION = 0.7
 
 
 def _round4(n):
@@ -168,13 +172,22 @@ class _Field(Function):
             view_dirs = view_dirs.contiguous().float()
             code = code.contiguous().float() if code is not None else None
         n_rays = view_dirs.shape[0] if use_color else 0
-        ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, mode, spec.flags, dev)
+        saved = None
+        if any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
+            nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), spec.flags)
+            # free = what the driver reports plus what torch's caching allocator holds but has not handed out
+            free = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            if 0 < nbytes <= SAVED_ACTIVATION_FRACTION * free:
+                saved = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        bwd_mode = _lib.MODE_BACKWARD if saved is not None else mode      # the saved layout needs the backward's workspace
+        ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, bwd_mode, spec.flags, dev)
         _lib.call("msdf_field_forward", sdf_d, enc_d, col_d, cd_d, _lib.ptr(x), M, _lib.ptr(view_dirs) if use_color else None,
                   n_rays, int(n_samples), _lib.ptr(code) if use_color else None, mode, float(clamp_radius), float(sphere_scale),
                   spec.flags, _lib.ptr(ws), ws.numel(), _lib.ptr(sdf), _lib.ptr(grad), _lib.ptr(feat), F_dim, _lib.ptr(rgb),
-                  _lib.stream())
+                  _lib.ptr(saved), saved.numel() if saved is not None else 0, _lib.stream())
         ctx.spec, ctx.kind, ctx.clamp, ctx.sphere_scale, ctx.n_samples, ctx.ns = spec, kind, clamp_radius, sphere_scale, n_samples, ns
         ctx.code_per_ray = code_per_ray
+        ctx.saved_acts = saved
         ctx.save_for_backward(x, view_dirs if use_color else None, code if use_color else None, table, offsets, rgb, *params)
         return sdf, grad, feat, rgb
 
@@ -202,11 +215,17 @@ class _Field(Function):
         F_dim = spec.sdf_spec.out_dims[-1] - 1
         n_rays = view_dirs.shape[0] if use_color else 0
         ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, _lib.MODE_BACKWARD, spec.flags, dev)
+        # the backward consumes (overwrites) the saved activations: a second backward through the same node recomputes.
+        # They were laid out for the forward's network (with the colour net for 'render'), so they are only usable
+        # when this backward sees the same one.
+        saved = ctx.saved_acts if (use_color or kind != "render") else None
+        ctx.saved_acts = None
         _lib.call("msdf_field_backward", sdf_d, enc_d, col_d, cd_d, _lib.ptr(x), M, _lib.ptr(view_dirs) if use_color else None,
                   n_rays, int(ctx.n_samples), _lib.ptr(code) if use_color else None, float(ctx.clamp), float(ctx.sphere_scale),
                   spec.flags, _lib.ptr(ws), ws.numel(), _lib.ptr(d_sdf), _lib.ptr(d_grad), _lib.ptr(d_feat), F_dim,
                   _lib.ptr(rgb) if use_color else None, _lib.ptr(d_rgb) if use_color else None, sdf_g, col_g,
-                  _lib.ptr(d_table), _lib.ptr(d_code), _lib.stream())
+                  _lib.ptr(d_table), _lib.ptr(d_code), _lib.ptr(saved), saved.numel() if saved is not None else 0, _lib.stream())
+        del saved
         return (None, None, None, None, None, None, None, d_code, d_table, None, *sdf_outs, *col_outs)
 
 

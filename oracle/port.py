@@ -564,7 +564,9 @@ def camera_rays(uv: Tensor, pose: Tensor, intrinsics: Tensor):
 # --------------------------------------------------------------------------------------
 def model_forward(params: Dict[str, Tensor], cfg: ModelCfg, inp: Dict[str, Tensor], indices: Tensor,
                   if_pixel_input: bool = False, training: bool = False, trace: Optional[dict] = None,
-                  eik_points: Optional[Tensor] = None):
+                  eik_points: Optional[Tensor] = None, z_vals: Optional[Tensor] = None):
+    """z_vals / eik_points: tests may inject the sample depths / eikonal points of the run under test, so that the
+    field, compositing and loss are compared on identical sample positions (the sampler has its own bit-exact test)."""
     if not if_pixel_input:
         ray_dirs, cam_loc = camera_rays(inp["uv"], inp["pose"], inp["intrinsics"])
         ray_dirs_tmp, _ = camera_rays(inp["uv"], torch.eye(4)[None], inp["intrinsics"])
@@ -577,8 +579,11 @@ def model_forward(params: Dict[str, Tensor], cfg: ModelCfg, inp: Dict[str, Tenso
     bsz, npix, _ = ray_dirs.shape
     ray_dirs = ray_dirs.reshape(-1, 3)
     beta0 = get_beta(params, cfg).detach()
-    z_vals, z_eik = sampler_get_z_vals(cfg, ray_dirs, cam_loc, lambda p: sdf_vals(params, cfg, p), beta0,
-                                       training, trace)
+    if z_vals is None:
+        z_vals, z_eik = sampler_get_z_vals(cfg, ray_dirs, cam_loc, lambda p: sdf_vals(params, cfg, p), beta0,
+                                           training, trace)
+    else:
+        z_eik = z_vals[:, :1]
     S = z_vals.shape[1]
     pts = (cam_loc.unsqueeze(1) + z_vals.unsqueeze(2) * ray_dirs.unsqueeze(1)).reshape(-1, 3)
     dirs = ray_dirs.unsqueeze(1).repeat(1, S, 1).reshape(-1, 3)
