@@ -40,7 +40,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=65536, help="rays per step PER GPU (weak scaling)")
     ap.add_argument("--config", default="mlp", choices=["mlp", "grid"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
+                    help="bf16: tcgen05 tensor-core mode (2e-2 parity, headline); fp32: SIMT mode (1e-4 parity)")
     ap.add_argument("--beta", type=float, default=0.01, help="density beta (0.01 -> 2 sampler rounds on the init sphere)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -238,13 +239,16 @@ def run_ours(args):
     ms_e2e = timed(e2e_step, args.steps)
     clk = clocks.stop() if rank == 0 else None
 
-    # one instrumented step: per-launch CUDA-event durations of the dominant kernel class (the MLP GEMMs)
+    # one instrumented step: per-launch CUDA-event durations (on the launching stream) of every instrumented kernel
+    # class; class 0 fp32 GEMM, 1 tcgen05 GEMM + weight gradient, 2 hash grid, 3 sampler, 4 compositing
     gemm_cls = 1 if args.precision == "bf16" else 0
     _lib.profile_read(0, reset=True)
     _lib.profile_enable(True)
     t_prof = timed(lambda: step(res, res_gt), 1)
     _lib.profile_enable(False)
-    g_ms, g_flops, g_n = _lib.profile_read(gemm_cls, reset=True)
+    prof = {c: _lib.profile_read(c, reset=False) for c in range(5)}
+    _lib.profile_read(0, reset=True)
+    g_ms, g_flops, g_n, g_bytes = prof[gemm_cls]
 
     if rank != 0:
         if world > 1:
@@ -255,26 +259,42 @@ def run_ours(args):
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
+    peak_bw = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "measured (MEASURED_PEAKS.json: bf16_tflops_sustained, hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)"
     achieved = (g_flops / 1e12) / (g_ms / 1e3) if g_ms > 0 else 0.0
+    gbs = (g_bytes / 1e9) / (g_ms / 1e3) if g_ms > 0 else 0.0
     table = GFLOP_PER_RAY_MLP if args.config == "mlp" else GFLOP_PER_RAY_GRID
     step_tf = table[min(max(rounds, 1), 5)] * 1e9 * n * args.steps / (ms / 1e3) / 1e12
     value = world * n * args.steps / (ms / 1e3)
+    traffic = None
+    tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes / launch of the same kernel from ncu --set full
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path)).get("tcgen05_gemm_dram_bytes_per_launch")
+    others = {}
+    for cls, name in ((2, "hash grid gather/scatter"), (3, "sampler round (warp scans)"), (4, "compositing fwd+bwd")):
+        k_ms, k_work, k_n, k_bytes = prof[cls]
+        if k_n:
+            others[name] = {"bound": "hbm", "achieved": (k_bytes / 1e9) / (k_ms / 1e3), "peak": peak_bw, "unit": "GB/s",
+                            "frac": (k_bytes / 1e9) / (k_ms / 1e3) / peak_bw, "launches": int(k_n), "ms_per_step": k_ms}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args), "rays_per_step_per_gpu": n, "sampler_rounds": rounds,
                    "precision_mode": args.precision, "parallelism": "ray-sharded dp%d, one NCCL all-reduce of the flat gradient arena" % world,
-                   "l2_policy": "inputs larger than L2: %.0f MB of activations per chunk stream through HBM every step" % (65536 * 19e3 / 1e6)},
+                   "l2_policy": "inputs larger than L2: every field chunk streams %.1f GB of activations through HBM (L2 is 126 MB)"
+                                % (min(n * 98, 262144) * 9.9e3 / 1e9)},
         "clocks": clk,
         "e2e": {"value": world * n * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "k_gemm (fp32 SIMT MLP sweeps)" if gemm_cls == 0 else "tcgen05 MLP GEMM",
+        "roofline": {"bound": "tensor", "kernel": "k_gemm (fp32 SIMT MLP sweeps)" if gemm_cls == 0 else "k_tc_gemm + k_tc_wgrad (tcgen05 MLP sweeps)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": None, "peak_source": peak_src, "launches": int(g_n), "kernel_ms_per_step": g_ms,
+                     "traffic": traffic, "peak_source": peak_src, "launches": int(g_n), "kernel_ms_per_step": g_ms,
                      "kernel_share_of_step": g_ms / t_prof if t_prof > 0 else None,
-                     "step_algorithmic_tflops": step_tf},
+                     "step_algorithmic_tflops": step_tf,
+                     # the bound that applies to a per-layer GEMM moving 1-2.5 KB per 131 KFLOP: algorithmic bytes / time
+                     "hbm_view": {"achieved": gbs, "peak": peak_bw, "unit": "GB/s", "frac": gbs / peak_bw if peak_bw else None},
+                     "other_kernels": others},
     }
     if world == 1 and not args.no_cpu_baseline and args.config == "mlp":
         cores = os.cpu_count() or 1

@@ -38,6 +38,7 @@ unsigned long long msdf_launch_count(void);
  * algorithmic bytes (the others) summed over the recorded launches. */
 int msdf_profile_enable(int on);
 int msdf_profile_read(int cls, double* total_ms, double* total_work, long long* count, int reset);
+int msdf_profile_read_bytes(int cls, double* total_bytes);   /* algorithmic bytes of the same launches */
 
 /* ------------------------------------------------------------------ ray sampler ---------------------------
  * ErrorBoundSampler.get_z_vals, model/ray_sampler.py:110-262, split at the SDF evaluations.

@@ -66,6 +66,7 @@ _SIGNATURES = {
     "msdf_tc_selftest": (c_int, [c_int, POINTER(c_float), _P]),
     "msdf_profile_enable": (c_int, [c_int]),
     "msdf_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int]),
+    "msdf_profile_read_bytes": (c_int, [c_int, POINTER(ctypes.c_double)]),
 }
 
 _lib = None
@@ -139,7 +140,9 @@ def profile_enable(on):
 
 
 def profile_read(cls, reset=False):
-    """(total_ms, total_work, count) of the recorded launches of one kernel class."""
-    ms, work, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+    """(total_ms, total_flops, count, total_algorithmic_bytes) of the recorded launches of one kernel class."""
+    ms, work, n, nbytes = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong(), ctypes.c_double()
+    torch.cuda.synchronize()
+    call("msdf_profile_read_bytes", int(cls), ctypes.byref(nbytes))
     call("msdf_profile_read", int(cls), ctypes.byref(ms), ctypes.byref(work), ctypes.byref(n), int(bool(reset)))
-    return ms.value, work.value, n.value
+    return ms.value, work.value, n.value, nbytes.value

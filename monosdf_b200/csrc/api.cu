@@ -19,14 +19,14 @@ extern "C" unsigned long long msdf_launch_count(void) { return g_msdf_launches; 
 // ---- per-launch timing -------------------------------------------------------------------------------------
 #include <vector>
 namespace {
-struct ProfRec { int cls; double work; cudaEvent_t a, b; };
+struct ProfRec { int cls; double work, bytes; cudaEvent_t a, b; };
 bool g_prof_on = false;
 std::vector<ProfRec> g_prof;
 }
 
-int msdf_prof_begin(int cls, double work, cudaStream_t st) {
+int msdf_prof_begin(int cls, double work, cudaStream_t st, double bytes) {
     if (!g_prof_on) return -1;
-    ProfRec r{cls, work, nullptr, nullptr};
+    ProfRec r{cls, work, bytes, nullptr, nullptr};
     if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return -1;
     cudaEventRecord(r.a, st);
     g_prof.push_back(r);
@@ -38,6 +38,13 @@ void msdf_prof_end(int slot, cudaStream_t st) {
 
 extern "C" int msdf_profile_enable(int on) {
     g_prof_on = on != 0;
+    return MSDF_OK;
+}
+// Sum of the algorithmic bytes of the recorded launches of class `cls` (call before a resetting msdf_profile_read).
+extern "C" int msdf_profile_read_bytes(int cls, double* total_bytes) {
+    double b = 0.0;
+    for (auto& r : g_prof) if (r.cls == cls) b += r.bytes;
+    if (total_bytes) *total_bytes = b;
     return MSDF_OK;
 }
 // Synchronises, sums the recorded launches of class `cls` (milliseconds, work units, count) and, when reset != 0,

@@ -51,5 +51,5 @@ extern unsigned long long g_msdf_launches;
 // Optional per-launch device timing (CUDA events on the launching stream) of the dominant kernels, read by
 // bench.py for the roofline line.  Disabled by default: msdf_prof_begin returns -1 and records nothing.
 enum { MSDF_PROF_GEMM_F32 = 0, MSDF_PROF_GEMM_TC = 1, MSDF_PROF_HASH = 2, MSDF_PROF_SAMPLER = 3, MSDF_PROF_RENDER = 4, MSDF_PROF_CLASSES = 5 };
-int msdf_prof_begin(int cls, double work, cudaStream_t st);
+int msdf_prof_begin(int cls, double work, cudaStream_t st, double bytes = 0.0);   // work: FLOPs; bytes: algorithmic bytes
 void msdf_prof_end(int slot, cudaStream_t st);

@@ -264,8 +264,11 @@ __global__ void k_hash_second_backward_grad(const float* __restrict__ gg_x, floa
 template <int C>
 int launch_forward(const float* x, const float* table, const int* offsets, float* out, int64_t out_ld, int level_major,
                    int64_t B, int L, float S, uint32_t H, float divide_factor, float* dy_dx, cudaStream_t st) {
+    // algorithmic bytes per point: 12 (x) + L*8 corners*C*4 (gathers) + L*C*4 (features) (+ L*3*C*4 when dy_dx is materialised)
+    const int prof = msdf_prof_begin(MSDF_PROF_HASH, 0.0, st, (double)B * (12.0 + L * C * 4.0 * 9.0 + (dy_dx ? L * C * 12.0 : 0.0)));
     k_hash_forward<C><<<(unsigned)msdf_div_up(B, 256), 256, 0, st>>>(x, table, offsets, out, out_ld, level_major, B, L, S, H,
                                                                     divide_factor, dy_dx);
+    msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH("msdf_hashgrid_forward");
     return MSDF_OK;
@@ -275,8 +278,11 @@ template <int C>
 int launch_scatter(const float* x, const int* offsets, int64_t B, int L, float S, uint32_t H, float divide_factor,
                    const float* grad, int64_t grad_ld, int glm, const float* grad2, int64_t grad2_ld, int g2lm,
                    const float* gg_x, float gg_scale, float* grad_table, cudaStream_t st) {
+    // per point: 12 (x) + L*C*4 (grad) + L*8*C*4*2 (read-modify-write of the gradient table)
+    const int prof = msdf_prof_begin(MSDF_PROF_HASH, 0.0, st, (double)B * (12.0 + L * C * 4.0 * (grad2 ? 2.0 : 1.0) + L * C * 64.0));
     k_hash_scatter<C><<<(unsigned)msdf_div_up(B, 256), 256, 0, st>>>(x, offsets, B, L, S, H, divide_factor, grad, grad_ld, glm,
                                                                     grad2, grad2_ld, g2lm, gg_x, gg_scale, grad_table);
+    msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH("msdf_hashgrid_scatter");
     return MSDF_OK;

@@ -538,6 +538,7 @@ struct EpiBase {
     // tcgen05 engine: number of valid columns of the 32-column chunk starting at n0 (<= 0: nothing to do)
     __device__ __forceinline__ int chunk_cols(int n0) const { const int nv = N - n0; return nv < 32 ? nv : 32; }
     static constexpr int kPre = 0;                 // epilogues that read operands back override kPre / prefetch
+    static constexpr int kStores = 1;              // bf16 matrices written per element (roofline accounting)
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
     __device__ __forceinline__ const float* colvec() const { return nullptr; }
 };
@@ -730,6 +731,7 @@ struct EpiTan : EpiBase<EpiTan<T>> {
         io.store(AZ, lda, n0, z, nv);
     }
     static constexpr int kPre = 2;
+    static constexpr int kStores = 2;
     __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
         if (n0 < this->N) { io.prefetch(Hn, ldh, n0, q); io.prefetch(AZ, lda, n0, q + 4); }
     }

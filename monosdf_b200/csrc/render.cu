@@ -204,9 +204,12 @@ extern "C" int msdf_render_forward(const float* z_vals, const float* sdf, const 
                    "msdf_render_forward: null pointer");
     MSDF_CHECK_ARG(n_samples >= 1, "msdf_render_forward: n_samples=%d", n_samples);
     MSDF_CHECK_ARG(!white_bkgd || bg_color, "msdf_render_forward: bg_color required with white_bkgd");
+    // algorithmic bytes per ray: S (z, sdf, rgb3, grad3) in, S weights + 7 floats out
+    const int prof = msdf_prof_begin(MSDF_PROF_RENDER, 0.0, (cudaStream_t)stream, (double)n_rays * (36.0 * n_samples + 28.0));
     k_render_forward<<<(unsigned)msdf_div_up(n_rays, kWarps), kWarps * 32, 0, (cudaStream_t)stream>>>(
         z_vals, sdf, rgb, grad, n_rays, n_samples, beta, depth_scale, depth_scale_stride, pose, pose_per_ray, white_bkgd, bg_color,
         weights, rgb_values, depth_values, normal_map);
+    msdf_prof_end(prof, (cudaStream_t)stream);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH("msdf_render_forward");
     return MSDF_OK;
@@ -227,9 +230,12 @@ extern "C" int msdf_render_backward(const float* z_vals, const float* sdf, const
         cudaError_t e = cudaFuncSetAttribute(k_render_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { msdf_set_error("msdf_render_backward: %zu B shared memory: %s", smem, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
     }
+    // per ray: S (z, sdf, rgb3, grad3, d_weights) in, S (d_sdf, d_rgb3, d_grad3) out
+    const int prof = msdf_prof_begin(MSDF_PROF_RENDER, 0.0, (cudaStream_t)stream, (double)n_rays * (64.0 * n_samples + 28.0));
     k_render_backward<<<(unsigned)msdf_div_up(n_rays, kWarps), kWarps * 32, smem, (cudaStream_t)stream>>>(
         z_vals, sdf, rgb, grad, n_rays, n_samples, beta, depth_scale, depth_scale_stride, pose, pose_per_ray, white_bkgd, bg_color,
         d_weights, d_rgb_values, d_depth_values, d_normal_map, d_sdf, d_rgb, d_grad, d_beta);
+    msdf_prof_end(prof, (cudaStream_t)stream);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH("msdf_render_backward");
     return MSDF_OK;

@@ -338,8 +338,12 @@ extern "C" int msdf_sampler_round(int64_t n_rays, int n_old, int n_new, float* z
     MSDF_CHECK_ARG(n_old == 0 || z_new, "msdf_sampler_round: z_new required when n_old > 0");
     size_t smem = (size_t)kWarpsPerBlock * 4 * cap * sizeof(float);
     int rc = set_smem(k_sampler_round, smem, "msdf_sampler_round"); if (rc) return rc;
+    // algorithmic bytes per ray: the old row (z, sdf) and the new samples in, the merged row out; work = software exps
+    const int prof = msdf_prof_begin(MSDF_PROF_SAMPLER, (double)n_rays * 3.0 * (beta_iters + 1) * (n_old + n_new), (cudaStream_t)stream,
+                                     (double)n_rays * 8.0 * (n_old + n_new + (n_old + n_new)));
     k_sampler_round<<<(unsigned)msdf_div_up(n_rays, kWarpsPerBlock), kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         n_rays, n_old, n_new, z, sdf, z_new, sdf_new, cap, beta0, eps, beta_iters, beta, flag);
+    msdf_prof_end(prof, (cudaStream_t)stream);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH("msdf_sampler_round");
     return MSDF_OK;

@@ -688,7 +688,9 @@ int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __
     }
     const int64_t tiles = (M + BM - 1) / BM;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st);
+    // algorithmic bytes: the A tile once, plus every bf16 operand the epilogue reads back and writes (epi.N real columns)
+    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
+                                     (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(Epi::kPre + Epi::kStores)));
     k_tc_gemm<Epi><<<grid, kThreads, smem, st>>>(mA, mW, M, BN, KB, stages, epi);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
@@ -725,7 +727,7 @@ int launch_wgrad(const __nv_bfloat16* X, int64_t ldx, int Ci, const __nv_bfloat1
         attr_set = true;
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st);
+    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st, (double)M * 2.0 * (double)(Ci + Cj));
     k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, epi);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();

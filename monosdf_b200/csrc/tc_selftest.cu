@@ -55,7 +55,7 @@ __global__ void k_maxerr(const float* a, const float* b, int64_t n, float* out) 
 
 struct EpiStore {     // C fp32: no coalescing helper for fp32 row stores; plain per-row writes are fine for a test
     float* C; int64_t ldc; int N;
-    static constexpr int kPre = 0;
+    static constexpr int kPre = 0; static constexpr int kStores = 1;
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
     __device__ __forceinline__ const float* colvec() const { return nullptr; }
     __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
@@ -67,7 +67,7 @@ struct EpiStore {     // C fp32: no coalescing helper for fp32 row stores; plain
 };
 struct EpiStoreBf16 {  // exercises WarpIO::load / store: C = bf16(acc + Cin)
     __nv_bfloat16* C; const __nv_bfloat16* Cin; int64_t ldc; int N;
-    static constexpr int kPre = 1;
+    static constexpr int kPre = 1; static constexpr int kStores = 1;
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO& io, int n0, uint4* q) const { if (n0 < N) io.prefetch(Cin, ldc, n0, q); }
     __device__ __forceinline__ const float* colvec() const { return nullptr; }
     __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
@@ -82,7 +82,7 @@ struct EpiStoreBf16 {  // exercises WarpIO::load / store: C = bf16(acc + Cin)
 };
 struct EpiAtomicAdd {
     float* C; int64_t ldc; int Ni, Nj;
-    static constexpr int kPre = 0;
+    static constexpr int kPre = 0; static constexpr int kStores = 1;
     __device__ __forceinline__ void prefetch(const msdf_tc::WarpIO&, int, uint4*) const {}
     __device__ __forceinline__ const float* colvec() const { return nullptr; }
     __device__ __forceinline__ void chunk(const msdf_tc::WarpIO& io, int n0, float v[32], const uint4* q) const {
