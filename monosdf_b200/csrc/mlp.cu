@@ -1149,15 +1149,24 @@ int gemm_nn(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t 
         return msdf_gemm::launch<kNN>(A, lda, n.W[l], n.ldw[l], Mc, n.in[l], n.out[l], 1, epi, c.st, what);
     }
 }
-// dW[rows, cols] += X^T Y, X [Mc, rows], Y [Mc, cols]
+template <class T>
+int colsum(const Ctx& c, const T* X, int64_t ldx, const T* w, int64_t ws, int64_t Mc, int N, float* out);
+
+// dW[rows, cols] += X^T Y, X [Mc, rows], Y [Mc, cols]; with db != nullptr also db[row(i)] += sum_m X[m, i] (the bias
+// gradient: in bf16 mode it rides along in the weight-gradient kernel, which has X in shared memory anyway)
 template <class T>
 int wgrad(const Ctx& c, const T* X, int64_t ldx, const T* Y, int64_t ldy, int rows, int cols, int64_t Mc, float* dW, int64_t ldw,
-          int perm_rows, int col_rot = 0) {
+          int perm_rows, int col_rot = 0, float* db = nullptr) {
     EpiAtomic e{};
     e.N = cols; e.C = dW; e.ldc = ldw; e.Mrows = rows; e.perm_rows = perm_rows; e.col_rot = col_rot;
     if constexpr (kIsBf16<T>) {
-        return msdf_tc::launch_wgrad(X, ldx, round_up(rows, 64), Y, ldy, round_up(cols, 64), Mc, e, c.st, "weight gradient");
+        return msdf_tc::launch_wgrad(X, ldx, round_up(rows, 64), Y, ldy, round_up(cols, 64), Mc, e, c.st, "weight gradient", db, rows,
+                                     perm_rows);
     } else {
+        if (db != nullptr) {
+            if (perm_rows > 0) { msdf_set_error("weight gradient: permuted bias sums are a bf16-mode feature"); return MSDF_ERR_UNSUPPORTED; }
+            RUN(colsum<T>(c, X, ldx, nullptr, 0, Mc, rows, db));
+        }
         const int tiles = (int)(msdf_div_up(rows, msdf_gemm::BM) * msdf_div_up(cols, msdf_gemm::BN));
         int splits = (int)((2 * 148 + tiles - 1) / tiles);
         const int64_t max_splits = msdf_div_up(Mc, 512);
@@ -1330,8 +1339,7 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
         // the 3-wide head as zero-padded tensor-core GEMMs: dpre [Mc, 64] is the operand of its wgrad and dgrad
         k_head_dpre<T><<<nblk(Mc, 128), 128, 0, c.st>>>(d_rgb, rgb, Mc, n.out[l], act, b.Hd, 64, 64);
         LAUNCHED("colour head dpre");
-        RUN(wgrad<T>(c, b.Hd, 64, b.C[l], b.ldc, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
-        RUN(colsum<T>(c, b.Hd, 64, nullptr, 0, Mc, n.out[l], gr->db[l]));
+        RUN(wgrad<T>(c, b.Hd, 64, b.C[l], b.ldc, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, 0, gr->db[l]));
         EpiBwdRelu<T> e{};
         e.Hin = b.C[l]; e.ldh = b.ldc; e.out = P; e.ldo = b.ldc;
         RUN((gemm_nn<T>(c, n, l, b.Hd, 64, Mc, e, "colour head dgrad")));
@@ -1346,8 +1354,7 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
     int pp = 0;
     for (l = n.L - 2; l >= 0; --l) {
         const int64_t ldin = l == 0 ? b.ldx : b.ldc;
-        RUN(wgrad<T>(c, P, b.ldc, b.C[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, l == 0 ? n.rot0 : 0));
-        RUN(colsum<T>(c, P, b.ldc, nullptr, 0, Mc, n.out[l], gr->db[l]));
+        RUN(wgrad<T>(c, P, b.ldc, b.C[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, l == 0 ? n.rot0 : 0, gr->db[l]));
         if (l > 0) {
             T* Pn = b.dC[pp ^ 1];
             EpiBwdRelu<T> e{};
@@ -1394,9 +1401,7 @@ int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, con
         // ---- last layer of the backward sweep: pbar_{L-1} = Dout
         if (kIsBf16<T>) {
             // Dout columns are [features..., sdf]: one weight-gradient GEMM with the row permutation folded in
-            RUN(wgrad<T>(c, b.Dout, b.ldo, b.H[L1], b.ldh, out_last, n.in[L1], Mc, gr->dW[L1], n.ldw[L1], out_last));
-            if (out_last > 1) RUN(colsum<T>(c, b.Dout, b.ldo, nullptr, 0, Mc, out_last - 1, gr->db[L1] + 1));
-            RUN(colsum<T>(c, b.Dout + (out_last - 1), b.ldo, nullptr, 0, Mc, 1, gr->db[L1]));
+            RUN(wgrad<T>(c, b.Dout, b.ldo, b.H[L1], b.ldh, out_last, n.in[L1], Mc, gr->dW[L1], n.ldw[L1], out_last, 0, gr->db[L1]));
         } else {
             RUN(colsum<T>(c, b.H[L1], b.ldh, b.Dout, b.ldo, Mc, n.in[L1], gr->dW[L1]));             // sdf row
             if (out_last > 1)
@@ -1407,8 +1412,7 @@ int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, con
     const T* P = b.Dout; int64_t ldp = b.ldo;
     for (int l = L1; l >= 0; --l) {
         if (l < L1) {
-            RUN(wgrad<T>(c, P, ldp, b.H[l], l == 0 ? b.d0p : b.ldh, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
-            RUN(colsum<T>(c, P, ldp, nullptr, 0, Mc, n.out[l], gr->db[l]));
+            RUN(wgrad<T>(c, P, ldp, b.H[l], l == 0 ? b.d0p : b.ldh, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, 0, gr->db[l]));
         }
         if (l == 0 && !(c.grid && grad_table)) break;
         EpiBwd<T> e{};

@@ -538,7 +538,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int BJ,
-           int64_t rows_per_split, int stages, Epi epi) {
+           int64_t rows_per_split, int stages, Epi epi, float* __restrict__ colsum, int colsum_n, int colsum_perm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -551,13 +551,15 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     const int i0 = blockIdx.x * 128, j0 = blockIdx.y * BJ;
     const int64_t r0 = (int64_t)blockIdx.z * rows_per_split;
     const int64_t r1 = (r0 + rows_per_split < Mrows) ? r0 + rows_per_split : Mrows;
+    const bool do_colsum = colsum != nullptr && blockIdx.y == 0;   // out[i] += sum_m X[m, i]: bias gradients for free
     const int nkb = r1 > r0 ? (int)((r1 - r0 + 63) / 64) : 0;   // the last block of a split may run past r1: the host
                                                                  // makes rows_per_split a multiple of 64, so only the
                                                                  // global tail is ragged and TMA zero-fills it
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
-        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+        // a stage is released by the MMA commit and, when the column sums of X ride along, by the 8 reducing warps
+        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), do_colsum ? 1 + kEpiWarps : 1); }
         mbar_init(smem_u32(&bars->tfull[0]), 1);
         fence_barrier_init();
     }
@@ -603,6 +605,36 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         }
         __syncwarp();
     } else if (nkb > 0) {
+        if (do_colsum) {
+            // While the MMAs run these 8 warps are idle: they read the X boxes of every stage out of shared memory
+            // (the operand is there anyway) and accumulate its column sums.  Thread t: column pair (t & 63) of the
+            // 128-column tile, k-rows 16 (t >> 6) .. +15 of the 64-row block; a warp reads whole 128-byte swizzle rows.
+            const int t = (int)threadIdx.x - 64;
+            const int pi = t & 63, g = t >> 6;
+            const int c = (pi & 31) * 2;
+            const uint32_t box_off = (uint32_t)(pi >> 5) * kBox;
+            float s0 = 0.f, s1 = 0.f;
+            int s = 0; uint32_t ph = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                if (lane == 0) mbar_wait(smem_u32(&bars->full[s]), ph);   // one poller per warp
+                __syncwarp();
+                const uint32_t st = base + s * stage_bytes + box_off;
+#pragma unroll
+                for (int kk = 0; kk < 16; ++kk) {
+                    const int k = g * 16 + kk;
+                    uint32_t w;
+                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(st + (uint32_t)(k * 128 + ((((c >> 3) ^ (k & 7)) << 4) | ((c & 7) * 2)))) : "memory");
+                    s0 += __uint_as_float(w << 16);
+                    s1 += __uint_as_float(w & 0xffff0000u);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->empty[s]));
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+            const int col = i0 + (pi >> 5) * 64 + c;
+            if (col < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col == colsum_perm - 1 ? 0 : col + 1) : col), s0);
+            if (col + 1 < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col + 1 == colsum_perm - 1 ? 0 : col + 2) : col + 1), s1);
+        }
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int chunks = (BJ + 31) / 32;
         mbar_wait(smem_u32(&bars->tfull[0]), 0);
@@ -702,7 +734,7 @@ int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __
 // of 64); the functor masks i / j beyond the real sizes and accumulates atomically.
 template <class Epi>
 int launch_wgrad(const __nv_bfloat16* X, int64_t ldx, int Ci, const __nv_bfloat16* Y, int64_t ldy, int Cj, int64_t M, const Epi& epi,
-                 cudaStream_t st, const char* what) {
+                 cudaStream_t st, const char* what, float* colsum = nullptr, int colsum_n = 0, int colsum_perm = 0) {
     if (M <= 0) return MSDF_OK;
     if (Ci % 64 != 0 || Cj % 64 != 0 || Ci <= 0 || Cj <= 0) { msdf_set_error("%s: wgrad needs column counts %% 64 == 0", what); return MSDF_ERR_ARG; }
     CUtensorMap mX, mY;
@@ -728,7 +760,7 @@ int launch_wgrad(const __nv_bfloat16* X, int64_t ldx, int Ci, const __nv_bfloat1
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st, (double)M * 2.0 * (double)(Ci + Cj));
-    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, epi);
+    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, epi, colsum, colsum_n, colsum_perm);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);

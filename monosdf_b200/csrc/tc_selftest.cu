@@ -42,6 +42,14 @@ __global__ void k_bf16_to_f32(const bf16* a, float* b, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) b[i] = __bfloat162float(a[i]);
 }
+// out[i] = sum_m X[m, i] (reference of the column sums that ride along in the weight-gradient kernel)
+__global__ void k_ref_colsum(const bf16* X, int64_t ldx, int64_t M, int N, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    float s = 0.f;
+    for (int64_t m = 0; m < M; ++m) s += __bfloat162float(X[m * ldx + i]);
+    out[i] = s;
+}
 __global__ void k_maxerr(const float* a, const float* b, int64_t n, float* out) {   // out[0] = max |a-b|, out[1] = max |b|
     float e = 0.f, r = 0.f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -162,8 +170,15 @@ extern "C" int msdf_tc_selftest(int variant, float* result_host, void* stream) {
         MSDF_CUDA_CALL(cudaMemsetAsync(C, 0, (int64_t)c.N * ldc * 4, st)); MSDF_CUDA_CALL(cudaMemsetAsync(out, 0, 8, st));
         k_ref_wgrad<<<(unsigned)msdf_div_up((int64_t)c.N * c.K, 128), 128, 0, st>>>(A, ldx, B, ldy, c.M, c.N, c.K, R, ldc);
         EpiAtomicAdd e{C, ldc, c.N, c.K};
-        rc = msdf_tc::launch_wgrad(A, ldx, c.Np, B, ldy, c.Kp, c.M, e, st, "msdf_tc_selftest(wgrad)");
+        float* cs = nullptr;   // [0, N): fused column sums, [N, 2N): reference
+        MSDF_CUDA_CALL(cudaMalloc(&cs, 2 * c.N * 4));
+        MSDF_CUDA_CALL(cudaMemsetAsync(cs, 0, 2 * c.N * 4, st));
+        k_ref_colsum<<<(unsigned)msdf_div_up(c.N, 128), 128, 0, st>>>(A, ldx, c.M, c.N, cs + c.N);
+        rc = msdf_tc::launch_wgrad(A, ldx, c.Np, B, ldy, c.Kp, c.M, e, st, "msdf_tc_selftest(wgrad)", cs, c.N, 0);
         if (!rc) k_maxerr<<<64, 256, 0, st>>>(C, R, (int64_t)c.N * ldc, out);
+        if (!rc) k_maxerr<<<1, 256, 0, st>>>(cs, cs + c.N, c.N, out);
+        cudaStreamSynchronize(st);
+        cudaFree(cs);
     }
     cudaError_t e2 = cudaStreamSynchronize(st);
     if (!rc && e2 != cudaSuccess) { msdf_set_error("msdf_tc_selftest: kernel failed: %s", cudaGetErrorString(e2)); rc = MSDF_ERR_CUDA; }
