@@ -203,6 +203,10 @@ int msdf_render_backward(const float* z_vals, const float* sdf, const float* rgb
 int msdf_weightnorm_forward(const float* g, const float* v, int out_dim, int in_dim, float* W, int ldw, void* stream);
 int msdf_weightnorm_backward(const float* g, const float* v, const float* dW, int ldw, int out_dim, int in_dim,
                              float* dg, float* dv, void* stream);
+/* Adjoint of the per-image appearance-code lookup embeddings[indices] (network.py:400-413): d_table[indices[r], :] +=
+ * d_code[r, :] with indices int64 [n_rays]; d_table [table_rows, code_dim] is accumulated into (caller zeroes). */
+int msdf_code_scatter(const float* d_code, const int64_t* indices, int64_t n_rays, int code_dim, int64_t table_rows,
+                      float* d_table, void* stream);
 /* torch.optim.Adam step (monosdf_train.py:210-221) over a flat arena; grad_scale folds the 1/world_size of
  * the gradient all-reduce.  step is the 1-based step count. */
 int msdf_fused_adam(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,

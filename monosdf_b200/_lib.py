@@ -62,6 +62,7 @@ _SIGNATURES = {
     "msdf_render_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "msdf_weightnorm_forward": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
     "msdf_weightnorm_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "msdf_code_scatter": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P]),
     "msdf_fused_adam": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),
     "msdf_tc_selftest": (c_int, [c_int, POINTER(c_float), _P]),
     "msdf_profile_enable": (c_int, [c_int]),

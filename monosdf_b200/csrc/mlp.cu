@@ -163,7 +163,7 @@ int check_tc_net(const Net& n, const char* who) {
     for (int l = 1; l < n.L; ++l)
         MSDF_CHECK_ARG(n.in[l] % 64 == 0 && n.in[l] <= 256, "%s: bf16 mode needs hidden widths that are multiples of 64 (<= 256); layer %d has %d",
                        who, l, n.in[l]);
-    MSDF_CHECK_ARG(n.in[0] <= 320 && n.out[n.L - 1] <= 320, "%s: bf16 mode supports at most 320 input / output columns", who);
+    MSDF_CHECK_ARG(n.in[0] <= 640 && n.out[n.L - 1] <= 320, "%s: bf16 mode supports at most 640 input / 320 output columns", who);
     return MSDF_OK;
 }
 
@@ -1124,6 +1124,22 @@ int gemm_nt(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t 
     epi.N = nrows;
     if constexpr (kIsBf16<T>) {
         const int kp = round_up(n.in[l], 64);
+        if (kp > 320) {
+            // a wide first layer (e.g. 321 colour inputs with the per-image code): its weights only fit in shared
+            // memory 128 rows at a time, so the layer runs as column blocks of the output
+            if constexpr (std::is_same<Epi, EpiRelu<T>>::value || std::is_same<Epi, EpiFwdAct<T>>::value || std::is_same<Epi, EpiBias<T>>::value) {
+                for (int q0 = 0; q0 < nrows; q0 += 128) {
+                    const int nb = nrows - q0 < 128 ? nrows - q0 : 128;
+                    Epi e = epi;
+                    e.N = nb; e.bias = epi.bias + q0; e.out = epi.out + q0;
+                    RUN(msdf_tc::launch_gemm(A, lda, Mc, kp, n.Wk[l] + (int64_t)(r0 + q0) * kp, kp, round_up(nb, 16), e, c.st, what));
+                }
+                return MSDF_OK;
+            } else {
+                msdf_set_error("%s: more than 320 input columns with this epilogue", what);
+                return MSDF_ERR_UNSUPPORTED;
+            }
+        }
         return msdf_tc::launch_gemm(A, lda, Mc, kp, n.Wk[l] + (int64_t)r0 * kp, kp, round_up(nrows, 16), epi, c.st, what);
     } else {
         return msdf_gemm::launch<kNT>(A, lda, n.W[l] + (int64_t)r0 * n.ldw[l], n.ldw[l], Mc, nrows, n.in[l], 1, epi, c.st, what);

@@ -698,8 +698,8 @@ template <class Epi>
 int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __nv_bfloat16* W, int64_t ldw, int BN, const Epi& epi,
                 cudaStream_t st, const char* what) {
     if (M <= 0) return MSDF_OK;
-    if (Kp % 64 != 0 || Kp <= 0 || Kp > 320 || BN % 16 != 0 || BN < 16 || BN > 256) {
-        msdf_set_error("%s: tensor-core GEMM needs K %% 64 == 0 (<= 320) and N %% 16 == 0 (<= 256); got K=%d N=%d", what, Kp, BN);
+    if (Kp % 64 != 0 || Kp <= 0 || Kp > 640 || BN % 16 != 0 || BN < 16 || BN > 256) {
+        msdf_set_error("%s: tensor-core GEMM needs K %% 64 == 0 (<= 640) and N %% 16 == 0 (<= 256); got K=%d N=%d", what, Kp, BN);
         return MSDF_ERR_ARG;
     }
     CUtensorMap mA, mW;

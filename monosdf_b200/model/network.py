@@ -229,6 +229,26 @@ class _Field(Function):
         return (None, None, None, None, None, None, None, d_code, d_table, None, *sdf_outs, *col_outs)
 
 
+class _CodeLookup(Function):
+    """embeddings[indices] (network.py:400-413) with a scatter backward that does not serialise on equal indices."""
+
+    @staticmethod
+    def forward(ctx, table, indices):
+        indices = indices.reshape(-1).long().contiguous()
+        ctx.save_for_backward(indices)
+        ctx.shape = table.shape
+        return table.detach()[indices]
+
+    @staticmethod
+    def backward(ctx, d_code):
+        (indices,) = ctx.saved_tensors
+        d_code = d_code.contiguous().float()
+        d_table = torch.zeros(ctx.shape, device=d_code.device, dtype=torch.float32)
+        _lib.call("msdf_code_scatter", _lib.ptr(d_code), _lib.ptr(indices), indices.shape[0], ctx.shape[1], ctx.shape[0],
+                  _lib.ptr(d_table), _lib.stream())
+        return d_table, None
+
+
 class _Composite(Function):
     """Laplace density + alpha compositing (density.py:21-30, network.py:626-640,552-562,603-616)."""
 
@@ -478,8 +498,9 @@ class RenderingNetwork(nn.Module):
         """[1,32] (one image, network.py:409) or [n_rays,32] (pixel mode, :411-412); None without per_image_code."""
         if not self.per_image_code:
             return None
-        code = self.embeddings[indices]
-        return code.reshape(-1, 32)
+        if self.embeddings.is_cuda:
+            return _CodeLookup.apply(self.embeddings, indices).reshape(-1, 32)
+        return self.embeddings[indices].reshape(-1, 32)     # CPU: parameter container only (no rendering path there)
 
     def forward(self, points, normals, view_dirs, feature_vectors, indices, if_pixel_input=False):
         raise NotImplementedError(

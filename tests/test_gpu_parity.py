@@ -307,3 +307,24 @@ def test_missing_extension_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libmonosdf_b200.so")
     with pytest.raises(RuntimeError, match="no CPU"):
         _lib.lib()
+
+
+def test_code_lookup_backward_matches_torch_indexing():
+    """Adjoint of embeddings[indices] (network.py:400-413): runs of equal indices, mixed indices, one ray."""
+    from monosdf_b200.model.network import _CodeLookup
+    g = torch.Generator().manual_seed(5)
+    table = torch.randn(1024, 32, generator=g).to(DEV)
+    for n, kind in [(1, "zeros"), (777, "zeros"), (5000, "runs"), (4096, "random")]:
+        if kind == "zeros":
+            idx = torch.zeros(n, dtype=torch.long)
+        elif kind == "runs":
+            idx = torch.randint(0, 1024, (n // 100 + 1,), generator=g).repeat_interleave(100)[:n]
+        else:
+            idx = torch.randint(0, 1024, (n,), generator=g)
+        idx = idx.to(DEV)
+        w = torch.randn(n, 32, generator=g).to(DEV)
+        t1 = table.clone().requires_grad_(True)
+        (_CodeLookup.apply(t1, idx) * w).sum().backward()
+        t2 = table.clone().requires_grad_(True)
+        (t2[idx] * w).sum().backward()
+        assert torch.allclose(t1.grad, t2.grad, rtol=1e-4, atol=1e-4), kind
