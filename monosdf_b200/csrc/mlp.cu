@@ -717,13 +717,14 @@ struct EpiTan : EpiBase<EpiTan<T>> {
     __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
-        float h[32], z[32];
-        io.unstage(q, h);
+        float z[32];
+        uint32_t hp[16];
+        io.unstage_packed(q, hp);
         io.unstage(q + 4, z);
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
             float s, d;
-            sig_dsig_from_h<true>(h[j] * hscale, s, d);
+            sig_dsig_from_h<true>(WarpIO::unpack(hp, j) * hscale, s, d);
             z[j] = v[j] * z[j] * d;
             v[j] = v[j] * s * tscale;
         }
@@ -781,11 +782,11 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
             io.store_f32(bh0, ldb, n0 - dh, r, nh > 0 ? nh : 0, nv, false);
         }
         if (nh > 0) {
-            float h[32], z[32];
-            io.unstage(q, h);
-            io.unstage(q + 4, z);
+            uint32_t hp[16], zp[16];
+            io.unstage_packed(q, hp);
+            io.unstage_packed(q + 4, zp);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(h[j] * hscale) + z[j];
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(WarpIO::unpack(hp, j) * hscale) + WarpIO::unpack(zp, j);
             io.store(PZ, ldp, n0, v, nh);
         }
     }

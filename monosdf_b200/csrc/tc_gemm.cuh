@@ -177,6 +177,7 @@ struct WarpIO {
     uint32_t trn;       // slot offset of piece lane&3 of row lane/4 (global side); rows +8 are 512 bytes further
     int rows_left;      // M - row0, clamped to [0, 32]
     mutable uint32_t flip;   // bf16 stagings alternate between the two 2 KB halves of the slot: one __syncwarp each
+    int64_t pf_row_shift;    // prefetch() addresses rows row0 + pf_row_shift (set while prefetching for the next tile)
 
     __device__ __forceinline__ void init() {
         const int x = (lane >> 1) & 3, r = lane >> 2, pc = lane & 3;
@@ -184,6 +185,7 @@ struct WarpIO {
         for (int p2 = 0; p2 < 4; ++p2) own[p2] = (uint32_t)(lane * 64 + ((p2 ^ x) << 4));
         trn = (uint32_t)(r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
         flip = 0u;
+        pf_row_shift = 0;
         retile(row0);
     }
     __device__ __forceinline__ void retile(int64_t new_row0) {
@@ -208,12 +210,15 @@ struct WarpIO {
     // are left undefined and must not be stored), unstage() transposes them through the slot so that
     // out[j] = P[row(), n0 + j].  Requires 16-byte aligned P + n0 and ld % 8 == 0.
     __device__ __forceinline__ void prefetch(const __nv_bfloat16* P, int64_t ld, int n0, uint4 q[4]) const {
-        const char* base = reinterpret_cast<const char*>(P + (row0 + (lane >> 2)) * ld + n0 + (lane & 3) * 8);
+        const int64_t base_row = row0 + pf_row_shift;        // pf_row_shift != 0: the same rows of a later tile
+        const int64_t left64 = M - base_row;
+        const int left = left64 < 0 ? 0 : (left64 > 32 ? 32 : (int)left64);
+        const char* base = reinterpret_cast<const char*>(P + (base_row + (lane >> 2)) * ld + n0 + (lane & 3) * 8);
         const int64_t step = ld * 16;            // 8 rows, in bytes
         const int r = lane >> 2;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const uint32_t on = (i * 8 + r) < rows_left ? 1u : 0u;
+            const uint32_t on = (i * 8 + r) < left ? 1u : 0u;
             asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.L1::no_allocate.v4.b32 {%0, %1, %2, %3}, [%4];\n\t}"
                          : "=r"(q[i].x), "=r"(q[i].y), "=r"(q[i].z), "=r"(q[i].w)
                          : "l"(base + i * step), "r"(on));
@@ -236,6 +241,21 @@ struct WarpIO {
                 out[p * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
             }
         }
+    }
+    // same, but the row stays packed: w[p * 4 + j] holds columns p*8 + 2j (low half) and p*8 + 2j + 1 (high half)
+    __device__ __forceinline__ void unstage_packed(const uint4 q[4], uint32_t w[16]) const {
+        const uint32_t h = slot + flip;
+        flip ^= 2048u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
+        __syncwarp();
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * p]), "=r"(w[4 * p + 1]), "=r"(w[4 * p + 2]), "=r"(w[4 * p + 3]) : "r"(h + own[p]) : "memory");
+    }
+    static __device__ __forceinline__ float unpack(const uint32_t w[16], int j) {      // column j of a packed row
+        return (j & 1) ? __uint_as_float(w[j >> 1] & 0xffff0000u) : __uint_as_float(w[j >> 1] << 16);
     }
     __device__ __forceinline__ void load(const __nv_bfloat16* P, int64_t ld, int n0, float out[32]) const {
         uint4 q[4];
@@ -377,6 +397,8 @@ constexpr int kMaxChunksPerWarp = 4;   // 256 accumulator columns / 32 / 2 warps
 // ==========================================================================================================
 // C = epi(A W^T), weights resident
 // ==========================================================================================================
+// 320 threads = 10 warps are allocated as 12 (granularity 4), so the register cap is 65536 / 384 = 168 per thread: the
+// epilogues keep their second read-back operand packed (unstage_packed) to stay below it without spilling
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, int64_t M, int BN, int KB,
@@ -499,8 +521,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         if (half + 2 * i < chunks) epi.prefetch(io, (half + 2 * i) * 32, pre[i]);
                 }
                 const bool has_next = tile + gridDim.x < num_tiles;
-                WarpIO io_next = io;
-                io_next.retile((tile + gridDim.x) * BM + q * 32);
                 mbar_wait(smem_u32(&bars->tfull[a]), aph);
                 tc_fence_after();
 #pragma unroll 1
@@ -516,7 +536,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                         if (ii == 0) {                                          // refill: chunk + kDepth of this tile ...
                             if (c + 2 * kDepth < chunks) epi.prefetch(io, (c + 2 * kDepth) * 32, pre[k]);
                         } else if (has_next && c - 2 * kDepth < chunks) {       // ... or the matching chunk of the next tile
-                            epi.prefetch(io_next, (c - 2 * kDepth) * 32, pre[k]);
+                            io.pf_row_shift = (int64_t)gridDim.x * BM;
+                            epi.prefetch(io, (c - 2 * kDepth) * 32, pre[k]);
+                            io.pf_row_shift = 0;
                         }
                     }
                 }
