@@ -136,6 +136,37 @@ def workspace(nbytes, device):
     return buf
 
 
+class _SavedPool:
+    """Recycles the multi-GB saved-activation buffers across training steps.  Handing them back to torch's caching
+    allocator lets it split the block for small tensors, and the next step's 30-60 GB request then falls through to a
+    synchronous cudaMalloc (measured: +70-90 ms on every other step)."""
+
+    def __init__(self):
+        self.free = []
+
+    def acquire(self, nbytes, device):
+        best = None
+        for i, t in enumerate(self.free):
+            if t.device == device and t.numel() >= nbytes and (best is None or t.numel() < self.free[best].numel()):
+                best = i
+        if best is not None and self.free[best].numel() <= 1.5 * nbytes + (64 << 20):
+            return self.free.pop(best)
+        return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+    def release(self, t):
+        if t is not None:
+            self.free.append(t)
+            if len(self.free) > 8:           # keep the few largest
+                self.free.sort(key=lambda x: -x.numel())
+                del self.free[8:]
+
+    def clear(self):
+        self.free.clear()
+
+
+saved_pool = _SavedPool()
+
+
 def profile_enable(on):
     call("msdf_profile_enable", int(bool(on)))
 

@@ -177,8 +177,9 @@ class _Field(Function):
             nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), spec.flags)
             # free = what the driver reports plus what torch's caching allocator holds but has not handed out
             free = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-            if 0 < nbytes <= SAVED_ACTIVATION_FRACTION * free:
-                saved = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+            pooled = sum(t.numel() for t in _lib.saved_pool.free if t.device == dev)
+            if 0 < nbytes <= SAVED_ACTIVATION_FRACTION * (free + pooled):
+                saved = _lib.saved_pool.acquire(nbytes, dev)
         bwd_mode = _lib.MODE_BACKWARD if saved is not None else mode      # the saved layout needs the backward's workspace
         ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, bwd_mode, spec.flags, dev)
         _lib.call("msdf_field_forward", sdf_d, enc_d, col_d, cd_d, _lib.ptr(x), M, _lib.ptr(view_dirs) if use_color else None,
@@ -218,13 +219,15 @@ class _Field(Function):
         # the backward consumes (overwrites) the saved activations: a second backward through the same node recomputes.
         # They were laid out for the forward's network (with the colour net for 'render'), so they are only usable
         # when this backward sees the same one.
-        saved = ctx.saved_acts if (use_color or kind != "render") else None
+        ctx_saved = ctx.saved_acts
+        saved = ctx_saved if (use_color or kind != "render") else None
         ctx.saved_acts = None
         _lib.call("msdf_field_backward", sdf_d, enc_d, col_d, cd_d, _lib.ptr(x), M, _lib.ptr(view_dirs) if use_color else None,
                   n_rays, int(ctx.n_samples), _lib.ptr(code) if use_color else None, float(ctx.clamp), float(ctx.sphere_scale),
                   spec.flags, _lib.ptr(ws), ws.numel(), _lib.ptr(d_sdf), _lib.ptr(d_grad), _lib.ptr(d_feat), F_dim,
                   _lib.ptr(rgb) if use_color else None, _lib.ptr(d_rgb) if use_color else None, sdf_g, col_g,
                   _lib.ptr(d_table), _lib.ptr(d_code), _lib.ptr(saved), saved.numel() if saved is not None else 0, _lib.stream())
+        _lib.saved_pool.release(ctx_saved)
         del saved
         return (None, None, None, None, None, None, None, d_code, d_table, None, *sdf_outs, *col_outs)
 
