@@ -17,6 +17,7 @@
 //   T = float          fp32 mode: SIMT FFMA GEMMs (gemm_f32.cuh), the reference's arithmetic class (1e-4 parity)
 //   T = __nv_bfloat16  bf16 mode: tcgen05 tensor-core GEMMs with TMEM accumulators and TMA-fed operands
 //                      (tc_gemm.cuh), activations stored in bf16, fp32 accumulation (2e-2 parity)
+#include <stdlib.h>
 #include <type_traits>
 
 #include "gemm_f32.cuh"
@@ -1090,10 +1091,17 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
     return c.off;
 }
 
+// Points per chunk in bf16 mode (experiment knob MSDF_CHUNK_POINTS; default 262144)
+inline int64_t chunk_cap_bf16() {
+    static int64_t v = 0;
+    if (!v) { const char* e = getenv("MSDF_CHUNK_POINTS"); v = e ? atoll(e) : 262144; if (v < 1024) v = 262144; }
+    return v;
+}
+
 // Chunking of the saved-activation mode: a function of the problem only, so that forward and backward agree.
 template <class T>
 int64_t saved_chunk(const Ctx& cx, int64_t M, int n_samples) {
-    const int64_t cap = kIsBf16<T> ? 262144 : 65536;   // the caps of pick_chunk
+    const int64_t cap = kIsBf16<T> ? chunk_cap_bf16() : 65536;   // the caps of pick_chunk
     int64_t mc = M < cap ? M : cap;
     if (cx.has_color && mc < M) mc = mc / n_samples * n_samples;
     return mc;
@@ -1107,8 +1115,8 @@ size_t saved_stride(const Ctx& cx, int64_t chunk) {
 
 template <class T>
 int64_t pick_chunk(const Ctx& cx, int64_t M, int mode, size_t ws_bytes) {
-    int64_t cap = kIsBf16<T> ? 262144 : 65536;
-    if (mode == MSDF_MODE_SDF_ONLY) cap = 524288;
+    int64_t cap = kIsBf16<T> ? chunk_cap_bf16() : 65536;
+    if (mode == MSDF_MODE_SDF_ONLY) cap = 2 * chunk_cap_bf16();
     int64_t mc = M < cap ? M : cap;
     mc = (mc + 127) / 128 * 128;
     while (mc > 128 && carve<T>(cx, mc, mode, nullptr, nullptr, nullptr, nullptr) > ws_bytes) mc = (mc / 2 + 127) / 128 * 128;

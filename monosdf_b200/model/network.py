@@ -11,6 +11,7 @@ double backward is an explicit tangent/backward sweep pair, replacing torch.auto
 There is no PyTorch/CPU fallback: without the CUDA library every forward raises.
 """
 import contextlib
+import os
 
 import numpy as np
 import torch
@@ -78,6 +79,19 @@ def _effective_weights(module, n_lin):
     return packs
 
 
+def _pose_from_quaternion(pose7):
+    """[B,7] (unit-normalised quaternion w,x,y,z + camera centre) -> [B,4,4] camera-to-world matrices."""
+    q = torch.nn.functional.normalize(pose7[:, :4].float(), dim=1)
+    w, x, y, z = q.unbind(dim=1)
+    rows = [1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+            2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+            2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]
+    p = torch.eye(4, device=pose7.device, dtype=torch.float32).repeat(pose7.shape[0], 1, 1)
+    p[:, :3, :3] = torch.stack(rows, dim=1).reshape(-1, 3, 3)
+    p[:, :3, 3] = pose7[:, 4:].float()
+    return p
+
+
 class _NetSpec:
     """Static geometry of one MLP as the C ABI wants it."""
 
@@ -132,7 +146,8 @@ class _FieldSpec:
 
 
 def _workspace_for(sdf_d, enc_d, col_d, cd_d, M, mode, flags, device):
-    cap = 524288 if mode == _lib.MODE_SDF_ONLY else (262144 if flags & _lib.FLAG_TENSOR_BF16 else 65536)
+    base = int(os.environ.get("MSDF_CHUNK_POINTS", "262144"))
+    cap = 2 * base if mode == _lib.MODE_SDF_ONLY else (base if flags & _lib.FLAG_TENSOR_BF16 else 65536)
     chunk = min(max(int(M), 128), cap)
     need = _lib.lib().msdf_field_workspace_bytes(sdf_d, enc_d, col_d, cd_d, chunk, mode, flags)
     if need == 0:
@@ -551,8 +566,9 @@ class MonoSDFNetwork(nn.Module):
             ray_dirs_tmp = input["ray_dirs_tmp"].reshape(-1, 3).contiguous().float()
             return ray_dirs, cam_loc, ray_dirs_tmp, 1, ray_dirs.shape[0]
         uv, pose, intrinsics = input["uv"], input["pose"], input["intrinsics"]
-        if pose.shape[1] == 7:
-            raise NotImplementedError("monosdf_b200: quaternion poses are not built; pass 4x4 matrices")
+        if pose.dim() == 2 and pose.shape[1] == 7:      # [qr, qi, qj, qk, tx, ty, tz] (rend_util.py:63-70, 121-138)
+            pose = _pose_from_quaternion(pose)
+        self._pose_matrix = pose
         B, N = uv.shape[0], uv.shape[1]
         dev = uv.device
         uv, pose, intrinsics = uv.contiguous().float(), pose.contiguous().float(), intrinsics.contiguous().float()
@@ -589,7 +605,7 @@ class MonoSDFNetwork(nn.Module):
             if if_pixel_input:
                 pose, pose_per_ray = input["ray_pose"], 1
             else:
-                pose, pose_per_ray = input["pose"][:1], 0
+                pose, pose_per_ray = self._pose_matrix[:1], 0
             weights, rgb_values, depth_values, normal_map = _Composite.apply(
                 z_vals, sdf.reshape(N, S), rgb_flat, grad, self.density.get_beta(), depth_scale, 3, pose, pose_per_ray,
                 self.white_bkgd, self.bg_color)

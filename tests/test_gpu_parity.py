@@ -328,3 +328,24 @@ def test_code_lookup_backward_matches_torch_indexing():
         t2 = table.clone().requires_grad_(True)
         (t2[idx] * w).sum().backward()
         assert torch.allclose(t1.grad, t2.grad, rtol=1e-4, atol=1e-4), kind
+
+
+def test_quaternion_pose_equals_matrix_pose(golden):
+    """rend_util.get_camera_params accepts [B,7] quaternion poses (:63-70); both forms must give the same rays."""
+    fx = golden("mlp_small")
+    model = build_model(fx, DEV).eval()
+    uv = torch.stack(torch.meshgrid(torch.arange(8.0), torch.arange(6.0), indexing="xy"), -1).reshape(1, -1, 2) * 40
+    K = torch.eye(4)[None].clone()
+    K[0, 0, 0] = K[0, 1, 1] = 300.0
+    K[0, 0, 2] = K[0, 1, 2] = 192.0
+    q = torch.nn.functional.normalize(torch.tensor([[0.9, 0.1, -0.3, 0.2]]), dim=1)
+    t = torch.tensor([[0.1, -0.2, 0.05]])
+    from monosdf_b200.model.network import _pose_from_quaternion
+    P = _pose_from_quaternion(torch.cat([q, t], 1))
+    assert torch.allclose(P[0, :3, :3] @ P[0, :3, :3].T, torch.eye(3), atol=1e-6)
+    idx = torch.zeros(1, dtype=torch.long, device=DEV)
+    with torch.no_grad():
+        a = model({"uv": uv.to(DEV), "intrinsics": K.to(DEV), "pose": torch.cat([q, t], 1).to(DEV)}, idx)
+        b = model({"uv": uv.to(DEV), "intrinsics": K.to(DEV), "pose": P.to(DEV)}, idx)
+    for k in ("rgb_values", "depth_values", "normal_map"):
+        assert torch.equal(a[k], b[k]), k
