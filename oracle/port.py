@@ -5,7 +5,7 @@ called only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` arm, always as the checker or the timed CPU baseline, never
 as the product path.
 
-Parity status: PINNED.  tests/test_oracle_vs_reference.py (container only) and the
+Parity status: PINNED.  tests/test_oracle_golden.py and the
 committed fixtures under tests/golden/ (made by oracle/make_golden.py from the
 unmodified reference at /root/reference) check every function here against the
 reference's own outputs on identical weights, rays and random draws.

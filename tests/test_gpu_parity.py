@@ -342,10 +342,10 @@ def test_quaternion_pose_equals_matrix_pose(golden):
     t = torch.tensor([[0.1, -0.2, 0.05]])
     from monosdf_b200.model.network import _pose_from_quaternion
     P = _pose_from_quaternion(torch.cat([q, t], 1))
-    assert torch.allclose(P[0, :3, :3] @ P[0, :3, :3].T, torch.eye(3), atol=1e-6)
+    assert torch.allclose(P[0, :3, :3] @ P[0, :3, :3].T, torch.eye(3), atol=1e-5)
     idx = torch.zeros(1, dtype=torch.long, device=DEV)
     with torch.no_grad():
         a = model({"uv": uv.to(DEV), "intrinsics": K.to(DEV), "pose": torch.cat([q, t], 1).to(DEV)}, idx)
         b = model({"uv": uv.to(DEV), "intrinsics": K.to(DEV), "pose": P.to(DEV)}, idx)
-    for k in ("rgb_values", "depth_values", "normal_map"):
-        assert torch.equal(a[k], b[k]), k
+    for k in ("rgb_values", "depth_values", "normal_map"):     # the matrix is built on the CPU here, on the GPU in the model
+        assert torch.allclose(a[k], b[k], rtol=1e-4, atol=1e-4), k
