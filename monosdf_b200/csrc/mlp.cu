@@ -718,19 +718,21 @@ struct EpiTan : EpiBase<EpiTan<T>> {
     __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
-        float z[32];
-        uint32_t hp[16];
+        uint32_t hp[16], ap[16];      // both operands stay packed; z is packed pair by pair (register budget: 168)
         io.unstage_packed(q, hp);
-        io.unstage(q + 4, z);
+        io.unstage_packed(q + 4, ap);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            float s, d;
-            sig_dsig_from_h<true>(WarpIO::unpack(hp, j) * hscale, s, d);
-            z[j] = v[j] * z[j] * d;
-            v[j] = v[j] * s * tscale;
+        for (int j = 0; j < 16; ++j) {
+            float s0, d0, s1, d1;
+            sig_dsig_from_h<true>(WarpIO::unpack(hp, 2 * j) * hscale, s0, d0);
+            sig_dsig_from_h<true>(WarpIO::unpack(hp, 2 * j + 1) * hscale, s1, d1);
+            const float z0 = v[2 * j] * WarpIO::unpack(ap, 2 * j) * d0, z1 = v[2 * j + 1] * WarpIO::unpack(ap, 2 * j + 1) * d1;
+            v[2 * j] = v[2 * j] * s0 * tscale;
+            v[2 * j + 1] = v[2 * j + 1] * s1 * tscale;
+            ap[j] = WarpIO::pack2(z0, z1);
         }
         io.store(Tout, ldt, n0, v, nv);
-        io.store(AZ, lda, n0, z, nv);
+        io.store_packed(AZ, lda, n0, ap, nv);
     }
     static constexpr int kPre = 2;
     static constexpr int kStores = 2;

@@ -264,19 +264,24 @@ struct WarpIO {
     }
 
     // P[row(), n0 + j] = v[j] for j < nvalid (<= 32); rows >= M are skipped
+    static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(lo, hi);
+        return *reinterpret_cast<const uint32_t*>(&hh);
+    }
     __device__ __forceinline__ void store(__nv_bfloat16* P, int64_t ld, int n0, const float v[32], int nvalid) const {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = pack2(v[2 * j], v[2 * j + 1]);
+        store_packed(P, ld, n0, w, nvalid);
+    }
+    // same with the row already packed (w[j] = columns 2j, 2j+1): lets an epilogue with two outputs pack one of them
+    // pair by pair while it computes, instead of holding 32 more floats
+    __device__ __forceinline__ void store_packed(__nv_bfloat16* P, int64_t ld, int n0, const uint32_t w[16], int nvalid) const {
         const uint32_t h = slot + flip;
         flip ^= 2048u;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            uint32_t w[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const __nv_bfloat162 hh = __floats2bfloat162_rn(v[p * 8 + 2 * j], v[p * 8 + 2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&hh);
-            }
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + own[p]), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-        }
+        for (int p = 0; p < 4; ++p)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + own[p]), "r"(w[4 * p]), "r"(w[4 * p + 1]), "r"(w[4 * p + 2]), "r"(w[4 * p + 3]) : "memory");
         __syncwarp();
         char* base = reinterpret_cast<char*>(P + (row0 + (lane >> 2)) * ld + n0 + (lane & 3) * 8);
         const int64_t step = ld * 16;
