@@ -213,6 +213,27 @@ int msdf_fused_adam(float* param, const float* grad, float* exp_avg, float* exp_
                     float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
                     void* stream);
 
+/* ------------------------------------------------------------------ loss ----------------------------------
+ * MonoSDFLoss.forward (model/loss.py:180-311, pixel-batch mode) and its gradient with respect to the renderer's
+ * outputs, fused: L1 / MSE colour (optionally through gamma2, :209-215), eikonal (:222-224), smoothness (:226-234),
+ * scale-and-shift-invariant depth (:29-49, :52-66, :236-243: target = 50 gt + 0.5, closed-form scale/shift over the
+ * masked batch), normal L1 + cosine (:245-250), foreground mask = gt mask & (ray's sdf row changes sign) (:274-276).
+ * No host synchronisation.  out[0..6] = loss, rgb, eikonal, smooth, depth, normal_l1, normal_cos; out[7] = number of
+ * masked rays.  d_* receive d loss / d input (written, not accumulated).  workspace: 32 + n_rays floats, 8-byte aligned. */
+typedef struct {
+    float eikonal_weight, smooth_weight, depth_weight, normal_l1_weight, normal_cos_weight;
+    float decay;                        /* exp(-step / end_step * 10) or 1 (:287-290) */
+    int32_t rgb_mse;                    /* 0: L1Loss (mean), 1: MSELoss (mean) */
+    int32_t gamma;                      /* if_gamma_loss */
+    int32_t scale_invariant_depth;      /* if_scale_invariant_depth */
+} msdf_loss_desc;
+int msdf_loss_forward_backward(const msdf_loss_desc* desc, int64_t n_rays, int n_samples, const float* rgb_values,
+                               const float* rgb_gt, const float* depth_values, const float* depth_gt, const float* gt_mask,
+                               const float* normal_map, const float* normal_gt, const float* sdf, int64_t n_eik,
+                               const float* grad_theta, const float* grad_theta_nei, float* workspace, float* out,
+                               float* d_rgb_values, float* d_depth_values, float* d_normal_map, float* d_grad_theta,
+                               float* d_grad_theta_nei, void* stream);
+
 /* ------------------------------------------------------------------ tensor-core path (bf16) ---------------
  * Self-test of the tcgen05 / TMEM / TMA GEMM engine (csrc/tc_gemm.cuh) against a naive kernel on the same bf16
  * inputs.  variant selects a shape (forward-type GEMMs and weight-gradient GEMMs, ragged sizes included);

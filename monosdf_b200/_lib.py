@@ -32,6 +32,12 @@ class EncodingDesc(Structure):
                 ("table", c_void_p), ("offsets", c_void_p)]
 
 
+class LossDesc(Structure):
+    _fields_ = [("eikonal_weight", c_float), ("smooth_weight", c_float), ("depth_weight", c_float),
+                ("normal_l1_weight", c_float), ("normal_cos_weight", c_float), ("decay", c_float),
+                ("rgb_mse", c_int32), ("gamma", c_int32), ("scale_invariant_depth", c_int32)]
+
+
 class ColorDesc(Structure):
     _fields_ = [("mode_idr", c_int32), ("multires_view", c_int32), ("feat_dim", c_int32), ("code_dim", c_int32),
                 ("code_per_ray", c_int32), ("final_act", c_int32)]
@@ -62,6 +68,8 @@ _SIGNATURES = {
     "msdf_render_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "msdf_weightnorm_forward": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
     "msdf_weightnorm_backward": (c_int, [_P, _P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "msdf_loss_forward_backward": (c_int, [POINTER(LossDesc), c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P, _P, _P, _P,
+                                           _P, _P, _P, _P, _P, _P]),
     "msdf_code_scatter": (c_int, [_P, _P, c_int64, c_int, c_int64, _P, _P]),
     "msdf_fused_adam": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),
     "msdf_tc_selftest": (c_int, [c_int, POINTER(c_float), _P]),

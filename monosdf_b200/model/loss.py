@@ -1,15 +1,53 @@
 """MonoSDFLoss, the consumer directly after the rendering path (reference code/model/loss.py:180-311).
 
-SURVEY.md section 8 row f1 ("next"): still plain torch ops here -- reductions over N rays -- but written without
-the reference's host synchronisations (`det.nonzero()` :44, `if divisor == 0` :57, the stray print :164), so the
-training step stays asynchronous.  Same loss terms and weights; pixel-batch mode only (the reference asserts
-that too, :167-168).
+SURVEY.md section 8 row f1: on CUDA tensors the loss and its gradient with respect to the renderer's outputs are ONE
+library call (msdf_loss_forward_backward, csrc/loss.cu: three launches, no host synchronisation) instead of the
+reference's ~40 small kernels, boolean-mask indexing and host syncs (`det.nonzero()` :44, `if divisor == 0` :57, the
+stray print :164).  `forward_torch` is the same loss in plain torch ops; it is what runs for CPU tensors (tests of the
+host logic) and what tests/ compare the fused kernel with.  Same loss terms and weights; pixel-batch mode only (the
+reference asserts that too, :167-168).
 """
 import math
 
 import torch
 import torch.nn.functional as F
 from torch import nn
+from torch.autograd import Function
+
+from .. import _lib
+
+
+class _FusedLoss(Function):
+    """(loss, terms[8]) = MonoSDFLoss(outputs, ground truth); gradients flow through `loss` only."""
+
+    @staticmethod
+    def forward(ctx, desc, rgb, depth, normal, sdf, g1, g2, rgb_gt, depth_gt, normal_gt, gt_mask):
+        dev = rgb.device
+        f = lambda t: t.detach().contiguous().float()
+        rgb, depth, normal, sdf = f(rgb), f(depth).reshape(-1), f(normal), f(sdf)
+        n, S = sdf.shape
+        n_eik = 0 if g1 is None else g1.shape[0]
+        g1c, g2c = (f(g1), f(g2)) if n_eik else (None, None)
+        ws = torch.empty(32 + n, device=dev)
+        out = torch.empty(8, device=dev)
+        d_rgb, d_depth, d_normal = torch.empty_like(rgb), torch.empty(n, device=dev), torch.empty_like(normal)
+        d_g1 = torch.empty_like(g1c) if n_eik else None
+        d_g2 = torch.empty_like(g2c) if n_eik else None
+        _lib.call("msdf_loss_forward_backward", desc, n, S, _lib.ptr(rgb), _lib.ptr(f(rgb_gt).reshape(-1, 3)), _lib.ptr(depth),
+                  _lib.ptr(f(depth_gt).reshape(-1)), _lib.ptr(f(gt_mask).reshape(-1)), _lib.ptr(normal),
+                  _lib.ptr(f(normal_gt).reshape(-1, 3)), _lib.ptr(sdf), n_eik, _lib.ptr(g1c), _lib.ptr(g2c), _lib.ptr(ws),
+                  _lib.ptr(out), _lib.ptr(d_rgb), _lib.ptr(d_depth), _lib.ptr(d_normal), _lib.ptr(d_g1), _lib.ptr(d_g2),
+                  _lib.stream())
+        ctx.save_for_backward(d_rgb, d_depth, d_normal, d_g1, d_g2)
+        terms = out.clone()
+        ctx.mark_non_differentiable(terms)
+        return out[0].clone(), terms
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_terms):
+        d_rgb, d_depth, d_normal, d_g1, d_g2 = ctx.saved_tensors
+        s = lambda t: None if t is None else t * g_loss
+        return (None, s(d_rgb), s(d_depth).reshape(-1, 1), s(d_normal), None, s(d_g1), s(d_g2), None, None, None, None)
 
 
 def compute_scale_and_shift_1D(prediction, target, mask):
@@ -55,6 +93,23 @@ class MonoSDFLoss(nn.Module):
         return torch.where(div > 0, num / div.clamp_min(1e-30), torch.zeros_like(num))
 
     def forward(self, model_outputs, ground_truth, if_pixel_input=False):
+        if not model_outputs["rgb_values"].is_cuda:
+            return self.forward_torch(model_outputs, ground_truth, if_pixel_input)
+        dev = model_outputs["rgb_values"].device
+        decay = math.exp(-self.step / self.end_step * 10.0) if self.end_step > 0 else 1.0
+        self.step += 1
+        d = _lib.LossDesc(self.eikonal_weight, self.smooth_weight, self.depth_weight, self.normal_l1_weight,
+                          self.normal_cos_weight, decay, int(isinstance(self.rgb_loss, nn.MSELoss)), int(self.if_gamma_loss),
+                          int(self.if_scale_invariant_depth))
+        has_eik = "grad_theta" in model_outputs
+        loss, t = _FusedLoss.apply(d, model_outputs["rgb_values"], model_outputs["depth_values"], model_outputs["normal_map"],
+                                   model_outputs["sdf"], model_outputs["grad_theta"] if has_eik else None,
+                                   model_outputs["grad_theta_nei"] if has_eik else None, ground_truth["rgb"].to(dev),
+                                   ground_truth["depth"].to(dev), ground_truth["normal"].to(dev), ground_truth["mask"].to(dev))
+        return {"loss": loss, "rgb_loss": t[1], "eikonal_loss": t[2], "smooth_loss": t[3], "depth_loss": t[4],
+                "normal_l1": t[5], "normal_cos": t[6]}
+
+    def forward_torch(self, model_outputs, ground_truth, if_pixel_input=False):
         dev = model_outputs["rgb_values"].device
         rgb_gt = ground_truth["rgb"].to(dev).reshape(-1, 3)
         depth_gt, normal_gt = ground_truth["depth"].to(dev), ground_truth["normal"].to(dev)
