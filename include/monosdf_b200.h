@@ -234,11 +234,13 @@ int msdf_loss_forward_backward(const msdf_loss_desc* desc, int64_t n_rays, int n
                                float* d_rgb_values, float* d_depth_values, float* d_normal_map, float* d_grad_theta,
                                float* d_grad_theta_nei, void* stream);
 
-/* ------------------------------------------------------------------ tensor-core path (bf16) ---------------
- * Self-test of the tcgen05 / TMEM / TMA GEMM engine (csrc/tc_gemm.cuh) against a naive kernel on the same bf16
- * inputs.  variant selects a shape (forward-type GEMMs and weight-gradient GEMMs, ragged sizes included);
+/* ------------------------------------------------------------------ tensor-core path (16-bit operands) -----
+ * Self-test of the tcgen05 / TMEM / TMA GEMM engine (csrc/tc_gemm.cuh) against a naive kernel on the same 16-bit
+ * inputs.  variant in [0, msdf_tc_selftest_count()) selects a shape and an operand-format combination (forward-type
+ * GEMMs and weight-gradient GEMMs, fp16 / bf16 / mixed operands, ragged sizes included);
  * result_host[0] = max |C - ref|, result_host[1] = max |ref| (HOST pointer, the call synchronises). */
 int msdf_tc_selftest(int variant, float* result_host, void* stream);
+int msdf_tc_selftest_count(void);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,24 @@ using msdf_gemm::kTN;
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr float kSqrt2 = 1.41421356237309504880f;
 
+using f16 = __half;
+
+// T is the MODE tag of the sweeps: float (fp32 mode) or bf16 (tensor-core mode).  In tensor-core mode the matrices
+// come in two 16-bit formats, both legal tcgen05.mma.kind::f16 operands in any combination:
+//   Fw<T> = fp16  "forward-like" values of bounded range where resolution matters: activations h_l, the reverse-sweep
+//                 state a_l, the colour-net rows and every weight copy (11 significant bits -> 8x smaller sdf /
+//                 grad error than bf16; stores saturate at +-65504)
+//   T     = bf16  adjoint / tangent values (t_l, z_l, pbar_l, output adjoints): linear in the upstream gradient,
+//                 hence of arbitrary scale -> they need fp32's exponent range
 template <class T> constexpr bool kIsBf16 = std::is_same<T, bf16>::value;
+template <class T> struct FwdOf { using type = T; };
+#ifndef MSDF_FWD_BF16
+template <> struct FwdOf<bf16> { using type = f16; };
+#endif
+template <class T> using Fw = typename FwdOf<T>::type;
+template <class E> struct Fmt16 { static constexpr int value = -1; };                  // fp32 mode: no 16-bit format
+template <> struct Fmt16<f16> { static constexpr int value = msdf_tc::kF16; };
+template <> struct Fmt16<bf16> { static constexpr int value = msdf_tc::kBF16; };
 
 // ----------------------------------------------------------------------------------------------------------
 // element access
@@ -48,6 +65,9 @@ __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16(v); }
+__device__ __forceinline__ float ldf(const f16* p) { return __half2float(*p); }
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.f), 65504.f); }
+__device__ __forceinline__ void stf(f16* p, float v) { *p = __float2half_rn(sat16(v)); }
 
 // W consecutive elements of a row; vectorised when the whole group is valid and 16-byte aligned
 template <int W>
@@ -71,6 +91,21 @@ __device__ __forceinline__ void load_row(const bf16* p, float* o, int nv) {
     for (int j = 0; j < W; ++j) o[j] = j < nv ? __bfloat162float(p[j]) : 0.f;
 }
 template <int W>
+__device__ __forceinline__ void load_row(const f16* p, float* o, int nv) {
+    if (W == 8 && nv == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o[2 * j] = msdf_tc::WarpIO::lo_of<msdf_tc::kF16>(w[j]);
+            o[2 * j + 1] = msdf_tc::WarpIO::hi_of<msdf_tc::kF16>(w[j]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) o[j] = j < nv ? __half2float(p[j]) : 0.f;
+}
+template <int W>
 __device__ __forceinline__ void store_row(float* p, const float* v, int nv) {
 #pragma unroll
     for (int j = 0; j < W; ++j)
@@ -91,6 +126,19 @@ __device__ __forceinline__ void store_row(bf16* p, const float* v, int nv) {
 #pragma unroll
     for (int j = 0; j < W; ++j)
         if (j < nv) p[j] = __float2bfloat16(v[j]);
+}
+template <int W>
+__device__ __forceinline__ void store_row(f16* p, const float* v, int nv) {
+    if (W == 8 && nv == 8 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = msdf_tc::WarpIO::pack2<msdf_tc::kF16>(v[2 * j], v[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j)
+        if (j < nv) stf(p + j, v[j]);
 }
 
 // activation math.  FAST = bf16 mode: branch-free MUFU ex2/lg2 approximations with flush-to-zero (error far below
@@ -129,8 +177,13 @@ struct Net {
     const float* W[MSDF_MAX_LAYERS];
     const float* b[MSDF_MAX_LAYERS];
     int maxw;
-    // bf16 copies for the tensor-core path (prepared per call): Wk = W (K-major over the inputs), Wt = W^T
-    bf16* Wk[MSDF_MAX_LAYERS]; bf16* Wt[MSDF_MAX_LAYERS];
+    // 16-bit copies for the tensor-core path (prepared per call): Wk = W (K-major over the inputs), Wt = W^T, each in
+    // the forward format (forward / reverse sweeps) and in bf16 (tangent / backward sweeps): one MMA takes both
+    // operands in the same format
+    Fw<bf16>* Wk[MSDF_MAX_LAYERS]; Fw<bf16>* Wt[MSDF_MAX_LAYERS];
+    bf16* Wkb[MSDF_MAX_LAYERS]; bf16* Wtb[MSDF_MAX_LAYERS];
+    const void* wk(int l, int fmt) const { return fmt == msdf_tc::kBF16 ? (const void*)Wkb[l] : (const void*)Wk[l]; }
+    const void* wt(int l, int fmt) const { return fmt == msdf_tc::kBF16 ? (const void*)Wtb[l] : (const void*)Wt[l]; }
     int perm_last;     // 1: rows of the last layer are ordered [features..., sdf] in Wk/Wt (bf16 SDF net)
     int rot0;          // bf16 copies of layer 0: input column k' holds W[:, (k' + rot0) % in] (rotated colour input)
 };
@@ -147,7 +200,7 @@ int make_net(const msdf_mlp_desc* d, Net& n, const char* who) {
     int w = 0;
     for (int l = 0; l < n.L; ++l) {
         n.in[l] = d->in_dim[l]; n.out[l] = d->out_dim[l]; n.ldw[l] = d->ldw[l]; n.W[l] = d->W[l]; n.b[l] = d->b[l];
-        n.Wk[l] = n.Wt[l] = nullptr;
+        n.Wk[l] = n.Wt[l] = nullptr; n.Wkb[l] = n.Wtb[l] = nullptr;
         MSDF_CHECK_ARG(n.W[l] && n.b[l], "%s: layer %d has null weights", who, l);
         MSDF_CHECK_ARG(n.ldw[l] >= n.in[l] && n.in[l] > 0 && n.out[l] > 0, "%s: layer %d bad dims", who, l);
         const int expect = (l == 0) ? n.d0 : (l == n.skip ? n.out[l - 1] + n.d0 : n.out[l - 1]);
@@ -548,7 +601,9 @@ using msdf_tc::WarpIO;
 
 template <class T>
 struct EpiFwdAct : EpiBase<EpiFwdAct<T>> {   // out[m,n] = softplus100(acc + b[n]) * oscale
-    const float* bias; T* out; int64_t ldo; float oscale;
+    using TF = Fw<T>;
+    static constexpr int FO = Fmt16<TF>::value;
+    const float* bias; TF* out; int64_t ldo; float oscale;
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         float o[W];
 #pragma unroll
@@ -567,13 +622,15 @@ struct EpiFwdAct : EpiBase<EpiFwdAct<T>> {   // out[m,n] = softplus100(acc + b[n
             const float p = v[j] + b[j];
             v[j] = fmaf(fast_lg2(1.0f + fast_ex2(-fabsf(p) * k100Log2e)), c2, fmaxf(p, 0.f) * os);
         }
-        io.store(out, ldo, n0, v, nv);
+        io.store<FO>(out, ldo, n0, v, nv);
     }
     __device__ __forceinline__ const float* colvec() const { return bias; }
 };
 template <class T>
 struct EpiBias : EpiBase<EpiBias<T>> {       // out[m,n] = acc + b[n]
-    const float* bias; T* out; int64_t ldo;
+    using TF = Fw<T>;
+    static constexpr int FO = Fmt16<TF>::value;
+    const float* bias; TF* out; int64_t ldo;
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         float o[W];
 #pragma unroll
@@ -588,13 +645,15 @@ struct EpiBias : EpiBase<EpiBias<T>> {       // out[m,n] = acc + b[n]
         io.colvec(n0, b);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += b[j];
-        io.store(out, ldo, n0, v, nv);
+        io.store<FO>(out, ldo, n0, v, nv);
     }
     __device__ __forceinline__ const float* colvec() const { return bias; }
 };
 template <class T>
 struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
-    const float* bias; T* out; int64_t ldo;
+    using TF = Fw<T>;
+    static constexpr int FO = Fmt16<TF>::value;
+    const float* bias; TF* out; int64_t ldo;
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         float o[W];
 #pragma unroll
@@ -609,7 +668,7 @@ struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
         io.colvec(n0, b);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + b[j], 0.f);
-        io.store(out, ldo, n0, v, nv);
+        io.store<FO>(out, ldo, n0, v, nv);
     }
     __device__ __forceinline__ const float* colvec() const { return bias; }
 };
@@ -642,8 +701,10 @@ struct EpiAtomic : EpiBase<EpiAtomic> {
 // reverse sweep, layer l: acc = (a_l W_l)[m,n], n over the layer's inputs
 template <class T>
 struct EpiRev : EpiBase<EpiRev<T>> {
-    const T* Hin; int64_t ldh; float hscale;       // stored input of layer l and the factor that undoes its scaling
-    T* Aout; int64_t lda;                          // a_{l-1}
+    using TF = Fw<T>;
+    static constexpr int FF = Fmt16<TF>::value;
+    const TF* Hin; int64_t ldh; float hscale;      // stored input of layer l and the factor that undoes its scaling
+    TF* Aout; int64_t lda;                         // a_{l-1}
     float* g0; int64_t ldg;
     int dh; float qscale;                          // skip layer: columns >= dh are the h0 half; both halves scaled 1/sqrt2
     int layer0, g0_accum;
@@ -684,10 +745,10 @@ struct EpiRev : EpiBase<EpiRev<T>> {
         }
         if (nh > 0) {
             float h[32];
-            io.unstage(q, h);
+            io.unstage<FF>(q, h);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(h[j] * hscale);
-            io.store(Aout, lda, n0, v, nh);
+            io.store<FF>(Aout, lda, n0, v, nh);
         }
     }
     static constexpr int kPre = 1;
@@ -698,8 +759,10 @@ struct EpiRev : EpiBase<EpiRev<T>> {
 // tangent sweep, layer l: acc = (t_l W_l^T)[m,n], n over the layer's outputs
 template <class T>
 struct EpiTan : EpiBase<EpiTan<T>> {
-    const T* Hn; int64_t ldh; float hscale;        // h_{l+1} as stored (input of layer l+1)
-    T* AZ; int64_t lda;                            // in: a_l, out: z_l
+    using TF = Fw<T>;
+    static constexpr int FF = Fmt16<TF>::value, FA = Fmt16<T>::value;
+    const TF* Hn; int64_t ldh; float hscale;       // h_{l+1} as stored (input of layer l+1)
+    TF* AZ; int64_t lda;                           // in: a_l (forward format), out: z_l (adjoint format), in place
     T* Tout; int64_t ldt; float tscale;
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         float h[W], a[W], t[W], z[W];
@@ -713,7 +776,7 @@ struct EpiTan : EpiBase<EpiTan<T>> {
             z[j] = v[j] * a[j] * d;
         }
         store_row<W>(Tout + m * ldt + n, t, nv);
-        store_row<W>(AZ + m * lda + n, z, nv);
+        store_row<W>(reinterpret_cast<T*>(AZ) + m * lda + n, z, nv);
     }
     __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
@@ -724,14 +787,14 @@ struct EpiTan : EpiBase<EpiTan<T>> {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             float s0, d0, s1, d1;
-            sig_dsig_from_h<true>(WarpIO::unpack(hp, 2 * j) * hscale, s0, d0);
-            sig_dsig_from_h<true>(WarpIO::unpack(hp, 2 * j + 1) * hscale, s1, d1);
-            const float z0 = v[2 * j] * WarpIO::unpack(ap, 2 * j) * d0, z1 = v[2 * j + 1] * WarpIO::unpack(ap, 2 * j + 1) * d1;
+            sig_dsig_from_h<true>(WarpIO::unpack<FF>(hp, 2 * j) * hscale, s0, d0);
+            sig_dsig_from_h<true>(WarpIO::unpack<FF>(hp, 2 * j + 1) * hscale, s1, d1);
+            const float z0 = v[2 * j] * WarpIO::unpack<FF>(ap, 2 * j) * d0, z1 = v[2 * j + 1] * WarpIO::unpack<FF>(ap, 2 * j + 1) * d1;
             v[2 * j] = v[2 * j] * s0 * tscale;
             v[2 * j + 1] = v[2 * j + 1] * s1 * tscale;
-            ap[j] = WarpIO::pack2(z0, z1);
+            ap[j] = WarpIO::pack2<FA>(z0, z1);
         }
-        io.store(Tout, ldt, n0, v, nv);
+        io.store<FA>(Tout, ldt, n0, v, nv);
         io.store_packed(AZ, lda, n0, ap, nv);
     }
     static constexpr int kPre = 2;
@@ -743,7 +806,9 @@ struct EpiTan : EpiBase<EpiTan<T>> {
 // backward sweep, layer l: acc = (pbar_l W_l)[m,n], n over the layer's inputs
 template <class T>
 struct EpiBwd : EpiBase<EpiBwd<T>> {
-    const T* Hin; int64_t ldh; float hscale;
+    using TF = Fw<T>;
+    static constexpr int FF = Fmt16<TF>::value, FA = Fmt16<T>::value;
+    const TF* Hin; int64_t ldh; float hscale;
     T* PZ; int64_t ldp;                            // in: z_{l-1}, out: pbar_{l-1}
     float* bh0; int64_t ldb;                       // adjoint of h_0 (hash-grid nets only), may be null
     int dh; float qscale; int layer0, bh0_accum;
@@ -789,8 +854,8 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
             io.unstage_packed(q, hp);
             io.unstage_packed(q + 4, zp);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(WarpIO::unpack(hp, j) * hscale) + WarpIO::unpack(zp, j);
-            io.store(PZ, ldp, n0, v, nh);
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(WarpIO::unpack<FF>(hp, j) * hscale) + WarpIO::unpack<FA>(zp, j);
+            io.store<FA>(PZ, ldp, n0, v, nh);
         }
     }
     static constexpr int kPre = 2;
@@ -800,7 +865,9 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
 };
 template <class T>
 struct EpiBwdRelu : EpiBase<EpiBwdRelu<T>> {  // colour net dgrad: out[m,n] = acc * [Hin[m,n] > 0]
-    const T* Hin; int64_t ldh; T* out; int64_t ldo;
+    using TF = Fw<T>;
+    static constexpr int FF = Fmt16<TF>::value, FA = Fmt16<T>::value;
+    const TF* Hin; int64_t ldh; T* out; int64_t ldo;
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         float h[W], o[W];
         load_row<W>(Hin + m * ldh + n, h, nv);
@@ -812,10 +879,10 @@ struct EpiBwdRelu : EpiBase<EpiBwdRelu<T>> {  // colour net dgrad: out[m,n] = ac
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         float h[32];
-        io.unstage(q, h);
+        io.unstage<FF>(q, h);
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = h[j] > 0.f ? v[j] : 0.f;
-        io.store(out, ldo, n0, v, nv);
+        io.store<FA>(out, ldo, n0, v, nv);
     }
     static constexpr int kPre = 1;
     __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
@@ -827,6 +894,7 @@ template <class T>
 struct EpiColorIn : EpiBase<EpiColorIn<T>> {
     int n_off;                                     // column offset of this launch (the tcgen05 engine splits N > 256)
     int nc, fc, F, cc, cd;                         // column of the normal (-1 = none), of feat, of the code
+    static constexpr int FA = Fmt16<T>::value;
     float* dn; T* Dout; int64_t ldo; int feat_col0; float* dcode; int64_t ldc;
     int rot, in0;                                  // GEMM column c is input column (c + rot) % in0 (bf16 mode: rot = fc)
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
@@ -845,8 +913,8 @@ struct EpiColorIn : EpiBase<EpiColorIn<T>> {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         const int g0c = n0 + n_off;                // first rotated column of the chunk
-        if (g0c + 32 <= F) { io.store(Dout, ldo, feat_col0 + g0c, v, 32); return; }
-        if (g0c < F) io.store(Dout, ldo, feat_col0 + g0c, v, F - g0c);
+        if (g0c + 32 <= F) { io.store<FA>(Dout, ldo, feat_col0 + g0c, v, 32); return; }
+        if (g0c < F) io.store<FA>(Dout, ldo, feat_col0 + g0c, v, F - g0c);
         if (cd > 0) {                              // code columns follow feat in the original order
             const int jlo = cc - rot - g0c;        // rotated column of code[0] is cc - rot
             io.store_f32(dcode, ldc, -jlo, v, jlo > 0 ? jlo : 0, jlo + cd < nv ? jlo + cd : nv, false);
@@ -961,21 +1029,22 @@ __global__ void k_code_grad(const float* __restrict__ dcode, int64_t n_rays, int
 
 // bf16 weight preparation for the tensor-core path.  Wk[r, k] = W[row(r), k] (zero padded to [rows_p, in_p]),
 // Wt[k, r] = W[row(r), k] (zero padded to [in_p16, rows_p64]); row(r) applies the [features..., sdf] permutation.
-__global__ void k_prep_weights(const float* __restrict__ W, int64_t ldw, int out, int in, int perm, int rot, bf16* __restrict__ Wk,
-                               int wk_rows, int wk_ld, bf16* __restrict__ Wt, int wt_rows, int wt_ld) {
+__global__ void k_prep_weights(const float* __restrict__ W, int64_t ldw, int out, int in, int perm, int rot, Fw<bf16>* __restrict__ Wk,
+                               int wk_rows, int wk_ld, Fw<bf16>* __restrict__ Wt, int wt_rows, int wt_ld, bf16* __restrict__ Wkb,
+                               bf16* __restrict__ Wtb) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nk = (int64_t)wk_rows * wk_ld, nt = (int64_t)wt_rows * wt_ld;
     if (i < nk) {
         const int r = (int)(i / wk_ld), k = (int)(i - (int64_t)r * wk_ld);
         float v = 0.f;
         if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + (k + rot) % in]; }
-        Wk[i] = __float2bfloat16(v);
+        stf(Wk + i, v); stf(Wkb + i, v);
     } else if (i < nk + nt) {
         const int64_t t = i - nk;
         const int k = (int)(t / wt_ld), r = (int)(t - (int64_t)k * wt_ld);
         float v = 0.f;
         if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + (k + rot) % in]; }
-        Wt[t] = __float2bfloat16(v);
+        stf(Wt + t, v); stf(Wtb + t, v);
     }
 }
 
@@ -1000,11 +1069,13 @@ ColorGeom color_geom(const msdf_color_desc* cd) {
 
 template <class T>
 struct Bufs {
-    T* H[MSDF_MAX_LAYERS];   // H[0] = encoded input (ld d0p); H[l] = input of layer l (ld ldh)
-    T* A[MSDF_MAX_LAYERS];   // a_l, later z_l / pbar_l  (l < L-1)
+    using TF = Fw<T>;
+    TF* H[MSDF_MAX_LAYERS];  // H[0] = encoded input (ld d0p); H[l] = input of layer l (ld ldh)
+    TF* A[MSDF_MAX_LAYERS];  // a_l (forward format), later z_l / pbar_l in the adjoint format T, in place  (l < L-1)
     T *TG0, *T2[2], *Dout;
     float *G0, *BH0, *dydx, *hashf, *sdf_raw, *mask, *dn, *dn_color, *gradc, *sdfc, *dcode;
-    T* X; T* C[MSDF_MAX_LAYERS]; T* dC[2]; T* Hd;   // Hd: colour head dpre, [Mc, 64] (bf16 mode)
+    TF* X; TF* C[MSDF_MAX_LAYERS]; T* dC[2]; T* Hd;   // Hd: colour head dpre, [Mc, 64] (bf16 mode)
+    T* adj(int l) const { return reinterpret_cast<T*>(A[l]); }   // A[l] once it holds z_l / pbar_l
     int64_t d0p, ldh, ldo, ldx, ldc;   // leading dimensions
 };
 
@@ -1037,32 +1108,35 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
     Carver c{(char*)ws, 0, ws == nullptr};
     Carver ps{(char*)saved, 0, saved == nullptr};
     Carver& p = split ? ps : c;
+    using TF = Fw<T>;
     Bufs<T> b{};
     if (kIsBf16<T>) {   // weight copies first (fixed size, independent of the chunk)
         Net* dst[2] = {sn_w, cn_w};
         const Net* src[2] = {&cx.sn, &cx.cn};
         for (int k = 0; k < (cx.has_color ? 2 : 1); ++k)
             for (int l = 0; l < src[k]->L; ++l) {
-                bf16* wk = c.take<bf16>(round_up(src[k]->out[l], 16), round_up(src[k]->in[l], 64));
-                bf16* wt = c.take<bf16>(round_up(src[k]->in[l], 16), round_up(src[k]->out[l], 64));
-                if (dst[k]) { dst[k]->Wk[l] = wk; dst[k]->Wt[l] = wt; }
+                Fw<bf16>* wk = c.take<Fw<bf16>>(round_up(src[k]->out[l], 16), round_up(src[k]->in[l], 64));
+                Fw<bf16>* wt = c.take<Fw<bf16>>(round_up(src[k]->in[l], 16), round_up(src[k]->out[l], 64));
+                bf16* wkb = c.take<bf16>(round_up(src[k]->out[l], 16), round_up(src[k]->in[l], 64));
+                bf16* wtb = c.take<bf16>(round_up(src[k]->in[l], 16), round_up(src[k]->out[l], 64));
+                if (dst[k]) { dst[k]->Wk[l] = wk; dst[k]->Wt[l] = wt; dst[k]->Wkb[l] = wkb; dst[k]->Wtb[l] = wtb; }
             }
     }
     const bool grid_feats = enc->grid_feat_dim > 0 && enc->table != nullptr;
     b.d0p = padw<T>(sn.d0); b.ldh = padw<T>(sn.maxw);
-    b.H[0] = p.take<T>(Mc, b.d0p);
+    b.H[0] = p.take<TF>(Mc, b.d0p);
     b.sdf_raw = c.take<float>(Mc, 1);
     if (grid_feats && kIsBf16<T>) b.hashf = c.take<float>(Mc, enc->grid_feat_dim);
     if (mode == MSDF_MODE_SDF_ONLY) {
-        T* pp[2] = {c.take<T>(Mc, b.ldh), c.take<T>(Mc, b.ldh)};
+        TF* pp[2] = {c.take<TF>(Mc, b.ldh), c.take<TF>(Mc, b.ldh)};
         for (int l = 1; l < sn.L; ++l) b.H[l] = pp[(l - 1) & 1];
     } else {
-        for (int l = 1; l < sn.L; ++l) b.H[l] = p.take<T>(Mc, b.ldh);
+        for (int l = 1; l < sn.L; ++l) b.H[l] = p.take<TF>(Mc, b.ldh);
         if (mode == MSDF_MODE_FORWARD && !split) {
-            T* pp[2] = {c.take<T>(Mc, b.ldh), c.take<T>(Mc, b.ldh)};
+            TF* pp[2] = {c.take<TF>(Mc, b.ldh), c.take<TF>(Mc, b.ldh)};
             for (int l = 0; l < sn.L - 1; ++l) b.A[l] = pp[l & 1];
         } else {
-            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = p.take<T>(Mc, b.ldh);
+            for (int l = 0; l < sn.L - 1; ++l) b.A[l] = p.take<TF>(Mc, b.ldh);
         }
         b.G0 = p.take<float>(Mc, round_up(sn.d0, 4));
         if (grid_feats) b.dydx = p.take<float>(Mc, enc->n_levels * 3 * enc->level_dim);
@@ -1078,9 +1152,9 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
         }
         if (cx.has_color) {
             b.ldx = padw<T>(cx.cg.in0); b.ldc = padw<T>(cx.cn.maxw);
-            b.X = p.take<T>(Mc, b.ldx);
+            b.X = p.take<TF>(Mc, b.ldx);
             b.C[0] = b.X;
-            for (int l = 1; l < cx.cn.L; ++l) b.C[l] = p.take<T>(Mc, b.ldc);
+            for (int l = 1; l < cx.cn.L; ++l) b.C[l] = p.take<TF>(Mc, b.ldc);
             if (mode == MSDF_MODE_BACKWARD) {
                 b.dC[0] = c.take<T>(Mc, b.ldc); b.dC[1] = c.take<T>(Mc, b.ldc);
                 if (kIsBf16<T>) b.Hd = c.take<T>(Mc, 64);
@@ -1130,10 +1204,12 @@ int64_t pick_chunk(const Ctx& cx, int64_t M, int mode, size_t ws_bytes) {
 // GEMM back ends
 // ----------------------------------------------------------------------------------------------------------
 // C = epi(A W_l^T) over output rows [r0, r0 + nrows) of W_l (in the bf16 copy's row order)
-template <class T, class Epi>
-int gemm_nt(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t Mc, int r0, int nrows, Epi epi, const char* what) {
+template <class T, class TA, class Epi>
+int gemm_nt(const Ctx& c, const Net& n, int l, const TA* A, int64_t lda, int64_t Mc, int r0, int nrows, Epi epi, const char* what) {
     epi.N = nrows;
     if constexpr (kIsBf16<T>) {
+        constexpr int fa = Fmt16<TA>::value;
+        const uint16_t* wk = reinterpret_cast<const uint16_t*>(n.wk(l, fa));
         const int kp = round_up(n.in[l], 64);
         if (kp > 320) {
             // a wide first layer (e.g. 321 colour inputs with the per-image code): its weights only fit in shared
@@ -1143,7 +1219,7 @@ int gemm_nt(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t 
                     const int nb = nrows - q0 < 128 ? nrows - q0 : 128;
                     Epi e = epi;
                     e.N = nb; e.bias = epi.bias + q0; e.out = epi.out + q0;
-                    RUN(msdf_tc::launch_gemm(A, lda, Mc, kp, n.Wk[l] + (int64_t)(r0 + q0) * kp, kp, round_up(nb, 16), e, c.st, what));
+                    RUN(msdf_tc::launch_gemm(A, fa, lda, Mc, kp, wk + (int64_t)(r0 + q0) * kp, fa, kp, round_up(nb, 16), e, c.st, what));
                 }
                 return MSDF_OK;
             } else {
@@ -1151,16 +1227,18 @@ int gemm_nt(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t 
                 return MSDF_ERR_UNSUPPORTED;
             }
         }
-        return msdf_tc::launch_gemm(A, lda, Mc, kp, n.Wk[l] + (int64_t)r0 * kp, kp, round_up(nrows, 16), epi, c.st, what);
+        return msdf_tc::launch_gemm(A, fa, lda, Mc, kp, wk + (int64_t)r0 * kp, fa, kp, round_up(nrows, 16), epi, c.st, what);
     } else {
         return msdf_gemm::launch<kNT>(A, lda, n.W[l] + (int64_t)r0 * n.ldw[l], n.ldw[l], Mc, nrows, n.in[l], 1, epi, c.st, what);
     }
 }
 // C = epi(A W_l): A [Mc, out_l] -> [Mc, in_l]
-template <class T, class Epi>
-int gemm_nn(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t Mc, Epi epi, const char* what) {
+template <class T, class TA, class Epi>
+int gemm_nn(const Ctx& c, const Net& n, int l, const TA* A, int64_t lda, int64_t Mc, Epi epi, const char* what) {
     epi.N = n.in[l];
     if constexpr (kIsBf16<T>) {
+        constexpr int fa = Fmt16<TA>::value;
+        const uint16_t* wt = reinterpret_cast<const uint16_t*>(n.wt(l, fa));
         const int kp = round_up(n.out[l], 64);
         const int np = round_up(n.in[l], 16);
         for (int c0 = 0; c0 < np; c0 += 256) {     // the accumulator holds at most 256 columns
@@ -1169,7 +1247,7 @@ int gemm_nn(const Ctx& c, const Net& n, int l, const T* A, int64_t lda, int64_t 
             e.N = n.in[l] - c0;
             if constexpr (std::is_same<Epi, EpiColorIn<T>>::value) e.n_off = c0;
             else if (c0 > 0) { msdf_set_error("%s: more than 256 output columns", what); return MSDF_ERR_UNSUPPORTED; }
-            RUN(msdf_tc::launch_gemm(A, lda, Mc, kp, n.Wt[l] + (int64_t)c0 * kp, kp, bn, e, c.st, what));
+            RUN(msdf_tc::launch_gemm(A, fa, lda, Mc, kp, wt + (int64_t)c0 * kp, fa, kp, bn, e, c.st, what));
         }
         return MSDF_OK;
     } else {
@@ -1181,14 +1259,14 @@ int colsum(const Ctx& c, const T* X, int64_t ldx, const T* w, int64_t ws, int64_
 
 // dW[rows, cols] += X^T Y, X [Mc, rows], Y [Mc, cols]; with db != nullptr also db[row(i)] += sum_m X[m, i] (the bias
 // gradient: in bf16 mode it rides along in the weight-gradient kernel, which has X in shared memory anyway)
-template <class T>
-int wgrad(const Ctx& c, const T* X, int64_t ldx, const T* Y, int64_t ldy, int rows, int cols, int64_t Mc, float* dW, int64_t ldw,
+template <class T, class TX, class TY>
+int wgrad(const Ctx& c, const TX* X, int64_t ldx, const TY* Y, int64_t ldy, int rows, int cols, int64_t Mc, float* dW, int64_t ldw,
           int perm_rows, int col_rot = 0, float* db = nullptr) {
     EpiAtomic e{};
     e.N = cols; e.C = dW; e.ldc = ldw; e.Mrows = rows; e.perm_rows = perm_rows; e.col_rot = col_rot;
     if constexpr (kIsBf16<T>) {
-        return msdf_tc::launch_wgrad(X, ldx, round_up(rows, 64), Y, ldy, round_up(cols, 64), Mc, e, c.st, "weight gradient", db, rows,
-                                     perm_rows);
+        return msdf_tc::launch_wgrad(X, Fmt16<TX>::value, ldx, round_up(rows, 64), Y, Fmt16<TY>::value, ldy, round_up(cols, 64), Mc, e, c.st,
+                                     "weight gradient", db, rows, perm_rows);
     } else {
         if (db != nullptr) {
             if (perm_rows > 0) { msdf_set_error("weight gradient: permuted bias sums are a bf16-mode feature"); return MSDF_ERR_UNSUPPORTED; }
@@ -1217,7 +1295,7 @@ int prep_weights(const Ctx& c, Net& n, int perm_last) {
         const int wt_rows = round_up(n.in[l], 16), wt_ld = round_up(n.out[l], 64);
         const int64_t total = (int64_t)wk_rows * wk_ld + (int64_t)wt_rows * wt_ld;
         k_prep_weights<<<nblk(total), 256, 0, c.st>>>(n.W[l], n.ldw[l], n.out[l], n.in[l], perm, l == 0 ? n.rot0 : 0, n.Wk[l], wk_rows, wk_ld, n.Wt[l],
-                                                     wt_rows, wt_ld);
+                                                     wt_rows, wt_ld, n.Wkb[l], n.Wtb[l]);
         LAUNCHED("weight prep");
     }
     return MSDF_OK;
@@ -1240,10 +1318,10 @@ int encode_chunk(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, boo
                                    want_dydx ? b.dydx : nullptr, c.st));
     }
     if (c.grid && !kIsBf16<T>) {   // the hash kernel already wrote its columns; PE only
-        k_encode<T><<<nblk(Mc * c.pe_w), 256, 0, c.st>>>(x, Mc, c.pe_w, 0, nullptr, b.H[0], b.d0p, c.pe_w);
+        k_encode<Fw<T>><<<nblk(Mc * c.pe_w), 256, 0, c.st>>>(x, Mc, c.pe_w, 0, nullptr, b.H[0], b.d0p, c.pe_w);
     } else {                       // PE + staged hash features (or zero features) + zero padding
         const int cols = (int)b.d0p;
-        k_encode_rows<T><<<nblk(Mc, 128), 128, 0, c.st>>>(x, Mc, c.enc->multires, c.pe_w, gw, c.grid ? b.hashf : nullptr, b.H[0], b.d0p, cols);
+        k_encode_rows<Fw<T>><<<nblk(Mc, 128), 128, 0, c.st>>>(x, Mc, c.enc->multires, c.pe_w, gw, c.grid ? b.hashf : nullptr, b.H[0], b.d0p, cols);
     }
     LAUNCHED("encode");
     return MSDF_OK;
@@ -1251,12 +1329,12 @@ int encode_chunk(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, boo
 
 // forward sweep; feat (ld ldf_) may be null
 template <class T>
-int forward_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc, T* feat, int64_t ldf_) {
+int forward_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc, Fw<T>* feat, int64_t ldf_) {
     const Net& n = c.sn;
     for (int l = 0; l < n.L - 1; ++l) {
         const int64_t ldin = l == 0 ? b.d0p : b.ldh;
         if (l + 1 == n.skip) {
-            k_skip_copy<T><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.H[0], b.d0p, b.H[l + 1], b.ldh, Mc, n.d0, n.out[l], kInvSqrt2);
+            k_skip_copy<Fw<T>><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.H[0], b.d0p, b.H[l + 1], b.ldh, Mc, n.d0, n.out[l], kInvSqrt2);
             LAUNCHED("skip copy");
         }
         EpiFwdAct<T> e{};
@@ -1264,7 +1342,7 @@ int forward_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc, T* feat, int64_t l
         RUN((gemm_nt<T>(c, n, l, b.H[l], ldin, Mc, 0, n.out[l], e, "sdf forward layer")));
     }
     const int l = n.L - 1;
-    k_rowdot<1, T><<<nblk(Mc, 8), 256, 0, c.st>>>(b.H[l], b.ldh, n.W[l], n.ldw[l], n.b[l], Mc, 1, n.in[l], kActNone, b.sdf_raw, 1);
+    k_rowdot<1, Fw<T>><<<nblk(Mc, 8), 256, 0, c.st>>>(b.H[l], b.ldh, n.W[l], n.ldw[l], n.b[l], Mc, 1, n.in[l], kActNone, b.sdf_raw, 1);
     LAUNCHED("sdf head");
     if (feat != nullptr && n.out[l] > 1) {
         EpiBias<T> e{};
@@ -1300,7 +1378,7 @@ int reverse_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc) {
     for (int l = n.L - 2; l >= 0; --l) {
         if (kIsBf16<T> && n.out[l] % 64 != 0) {   // K padding of the operand must be finite (zero)
             const int w = round_up(n.out[l], 64) - n.out[l];
-            k_zero_cols<T><<<nblk(Mc * w), 256, 0, c.st>>>(b.A[l], b.ldh, Mc, n.out[l], w);
+            k_zero_cols<Fw<T>><<<nblk(Mc * w), 256, 0, c.st>>>(b.A[l], b.ldh, Mc, n.out[l], w);
             LAUNCHED("zero operand padding");
         }
         RUN((gemm_nn<T>(c, n, l, b.A[l], b.ldh, Mc, make_rev<T>(n, b, l), "sdf reverse layer")));
@@ -1327,11 +1405,11 @@ int color_forward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, co
     // chunks start on a ray boundary; view / code pointers are already offset to the chunk's first ray
     if (kIsBf16<T> && n.rot0 == g.fc && c.cd->feat_dim % 8 == 0) {
         // rotated row: [feat | code | x | PE(view) | normal | padding]: everything after feat is one aligned range
-        k_color_input_rows<T><<<nblk(Mc, 128), 128, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, c.cd->multires_view,
+        k_color_input_rows<Fw<T>><<<nblk(Mc, 128), 128, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, c.cd->multires_view,
                                                               g.pe_w, c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, c.cd->feat_dim,
                                                               (int)b.ldx);
     } else {
-        k_color_input<T><<<nblk(Mc * cols), 256, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, g.pe_w, c.cd->feat_dim,
+        k_color_input<Fw<T>><<<nblk(Mc * cols), 256, 0, c.st>>>(x, view, normal, code, Mc, n_samples, c.cd->mode_idr, g.pe_w, c.cd->feat_dim,
                                                            c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, pad, n.rot0);
     }
     LAUNCHED("colour input");
@@ -1349,7 +1427,7 @@ int color_forward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, co
         RUN((gemm_nt<T>(c, n, l, b.C[l], b.ldc, Mc, 0, n.out[l], e, "colour head")));
         return MSDF_OK;
     }
-    k_rowdot<4, T><<<nblk(Mc, 8), 256, 0, c.st>>>(b.C[l], b.ldc, n.W[l], n.ldw[l], n.b[l], Mc, n.out[l], n.in[l],
+    k_rowdot<4, Fw<T>><<<nblk(Mc, 8), 256, 0, c.st>>>(b.C[l], b.ldc, n.W[l], n.ldw[l], n.b[l], Mc, n.out[l], n.in[l],
                                                  c.cd->final_act == 0 ? kActSigmoid : kActRelu, rgb, n.out[l]);
     LAUNCHED("colour head");
     return MSDF_OK;
@@ -1409,7 +1487,7 @@ int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, con
             k_skip_copy<T><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.TG0, b.d0p, Tin, ldt, Mc, n.d0, n.in[l] - n.d0, kInvSqrt2);
             LAUNCHED("tangent skip copy");
         }
-        RUN(wgrad<T>(c, b.A[l], b.ldh, Tin, ldt, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+        RUN(wgrad<T>(c, b.A[l], b.ldh, Tin, ldt, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));   // a_l still in A[l]
         T* Tout = b.T2[(l + 1) & 1];
         EpiTan<T> e{};
         e.Hn = b.H[l + 1]; e.ldh = b.ldh; e.hscale = in_scale(n, l + 1); e.AZ = b.A[l]; e.lda = b.ldh;
@@ -1426,7 +1504,7 @@ int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, con
         }
         RUN(colsum<T>(c, Tin, ldt, nullptr, 0, Mc, n.in[L1], gr->dW[L1]));                          // a_{L-1} = e_0 -> sdf row
         // ---- last layer of the backward sweep: pbar_{L-1} = Dout
-        if (kIsBf16<T>) {
+        if constexpr (kIsBf16<T>) {
             // Dout columns are [features..., sdf]: one weight-gradient GEMM with the row permutation folded in
             RUN(wgrad<T>(c, b.Dout, b.ldo, b.H[L1], b.ldh, out_last, n.in[L1], Mc, gr->dW[L1], n.ldw[L1], out_last, 0, gr->db[L1]));
         } else {
@@ -1444,13 +1522,13 @@ int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, con
         if (l == 0 && !(c.grid && grad_table)) break;
         EpiBwd<T> e{};
         e.Hin = b.H[l]; e.ldh = l == 0 ? b.d0p : b.ldh; e.hscale = in_scale(n, l);
-        e.PZ = l > 0 ? b.A[l - 1] : nullptr; e.ldp = b.ldh;
+        e.PZ = l > 0 ? b.adj(l - 1) : nullptr; e.ldp = b.ldh;
         e.bh0 = (c.grid && grad_table) ? b.BH0 : nullptr; e.ldb = round_up(n.d0, 4);
         e.dh = l == n.skip ? n.in[l] - n.d0 : n.in[l];
         e.qscale = l == n.skip ? kInvSqrt2 : 1.0f;
         e.layer0 = l == 0; e.bh0_accum = n.skip > 0;
         RUN((gemm_nn<T>(c, n, l, P, ldp, Mc, e, "sdf backward layer")));
-        if (l > 0) { P = b.A[l - 1]; ldp = b.ldh; }
+        if (l > 0) { P = b.adj(l - 1); ldp = b.ldh; }
     }
     if (c.grid && grad_table) {
         const int64_t ldg = round_up(n.d0, 4);
@@ -1539,9 +1617,9 @@ int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int
         if (saving && m0 > 0)   // this chunk's slice of the saved buffer (the workspace part is reused)
             carve<T>(c, (chunk + 127) / 128 * 128, mode, workspace, &b, nullptr, nullptr, (char*)saved + stride * (size_t)(m0 / chunk), true);
         RUN(encode_chunk<T>(c, b, xc, Mc, with_grad));
-        T* featc = nullptr; int64_t ldf_ = 0;
+        Fw<T>* featc = nullptr; int64_t ldf_ = 0;
         if (c.has_color) { featc = b.X + (kIsBf16<T> ? 0 : c.cg.fc); ldf_ = b.ldx; }
-        else if (feat != nullptr) { featc = reinterpret_cast<T*>(feat + m0 * ld_feat); ldf_ = ld_feat; }
+        else if (feat != nullptr) { featc = reinterpret_cast<Fw<T>*>(feat + m0 * ld_feat); ldf_ = ld_feat; }
         RUN(forward_sweep<T>(c, b, Mc, featc, ldf_));
         if (with_grad) RUN(reverse_sweep<T>(c, b, Mc));
         RUN(decode_chunk<T>(c, b, xc, Mc, with_grad, sdf ? sdf + m0 : nullptr, with_grad ? grad + 3 * m0 : nullptr,

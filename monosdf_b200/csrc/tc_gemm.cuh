@@ -20,6 +20,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
@@ -153,9 +154,20 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
     d |= (uint64_t)2 << 61;     // layout_type_ = SWIZZLE_128B
     return d;
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M x N, operand majors
-__host__ __device__ inline uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+// instruction descriptor (cute::UMMA::InstrDescriptor): 16-bit x 16-bit -> fp32, M x N, operand majors
+// 16-bit operand formats of tcgen05.mma.kind::f16 (the a_format / b_format fields of the instruction descriptor).
+// The field sweeps keep "forward-like" matrices (activations h, reverse-sweep state a, colour rows) in fp16
+// (11 significant bits: 8x smaller sdf error than bf16) and the wide-range adjoint / tangent
+// matrices in bf16.  Both operands of one MMA must have the SAME format (a mixed descriptor raises an illegal
+// instruction on B200, measured), so the weights exist in both formats and the weight-gradient kernel converts its
+// fp16 operand to bf16 in shared memory.
+enum Fmt : int { kF16 = 0, kBF16 = 1 };
+template <class E> struct FmtOf;
+template <> struct FmtOf<__half> { static constexpr int value = kF16; };
+template <> struct FmtOf<__nv_bfloat16> { static constexpr int value = kBF16; };
+
+__host__ __device__ inline uint32_t instr_desc(int M, int N, int a_mn_major, int b_mn_major, int a_fmt, int b_fmt) {
+    return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -209,7 +221,8 @@ struct WarpIO {
     // hidden: prefetch() issues the loads (lane t fetches 16-byte piece t&3 of rows i*8 + t/4; predicated, rows >= M
     // are left undefined and must not be stored), unstage() transposes them through the slot so that
     // out[j] = P[row(), n0 + j].  Requires 16-byte aligned P + n0 and ld % 8 == 0.
-    __device__ __forceinline__ void prefetch(const __nv_bfloat16* P, int64_t ld, int n0, uint4 q[4]) const {
+    __device__ __forceinline__ void prefetch(const void* Pv, int64_t ld, int n0, uint4 q[4]) const {
+        const uint16_t* P = reinterpret_cast<const uint16_t*>(Pv);     // any 16-bit element type
         const int64_t base_row = row0 + pf_row_shift;        // pf_row_shift != 0: the same rows of a later tile
         const int64_t left64 = M - base_row;
         const int left = left64 < 0 ? 0 : (left64 > 32 ? 32 : (int)left64);
@@ -224,6 +237,15 @@ struct WarpIO {
                          : "l"(base + i * step), "r"(on));
         }
     }
+    template <int F>
+    static __device__ __forceinline__ float lo_of(uint32_t w) {
+        return F == kBF16 ? __uint_as_float(w << 16) : __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+    }
+    template <int F>
+    static __device__ __forceinline__ float hi_of(uint32_t w) {
+        return F == kBF16 ? __uint_as_float(w & 0xffff0000u) : __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+    }
+    template <int F>
     __device__ __forceinline__ void unstage(const uint4 q[4], float out[32]) const {
         const uint32_t h = slot + flip;
         flip ^= 2048u;
@@ -237,8 +259,8 @@ struct WarpIO {
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(h + own[p]) : "memory");
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                out[p * 8 + 2 * j] = __uint_as_float(w[j] << 16);
-                out[p * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+                out[p * 8 + 2 * j] = lo_of<F>(w[j]);
+                out[p * 8 + 2 * j + 1] = hi_of<F>(w[j]);
             }
         }
     }
@@ -254,29 +276,39 @@ struct WarpIO {
         for (int p = 0; p < 4; ++p)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * p]), "=r"(w[4 * p + 1]), "=r"(w[4 * p + 2]), "=r"(w[4 * p + 3]) : "r"(h + own[p]) : "memory");
     }
+    template <int F>
     static __device__ __forceinline__ float unpack(const uint32_t w[16], int j) {      // column j of a packed row
-        return (j & 1) ? __uint_as_float(w[j >> 1] & 0xffff0000u) : __uint_as_float(w[j >> 1] << 16);
+        return (j & 1) ? hi_of<F>(w[j >> 1]) : lo_of<F>(w[j >> 1]);
     }
-    __device__ __forceinline__ void load(const __nv_bfloat16* P, int64_t ld, int n0, float out[32]) const {
+    template <int F>
+    __device__ __forceinline__ void load(const void* P, int64_t ld, int n0, float out[32]) const {
         uint4 q[4];
         prefetch(P, ld, n0, q);
-        unstage(q, out);
+        unstage<F>(q, out);
     }
 
     // P[row(), n0 + j] = v[j] for j < nvalid (<= 32); rows >= M are skipped
+    template <int F>
     static __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-        const __nv_bfloat162 hh = __floats2bfloat162_rn(lo, hi);
-        return *reinterpret_cast<const uint32_t*>(&hh);
+        if (F == kBF16) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(lo, hi);
+            return *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        uint32_t w;                           // fp16 saturates to +-65504 instead of overflowing to inf
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+        return w;
     }
-    __device__ __forceinline__ void store(__nv_bfloat16* P, int64_t ld, int n0, const float v[32], int nvalid) const {
+    template <int F>
+    __device__ __forceinline__ void store(void* P, int64_t ld, int n0, const float v[32], int nvalid) const {
         uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = pack2(v[2 * j], v[2 * j + 1]);
+        for (int j = 0; j < 16; ++j) w[j] = pack2<F>(v[2 * j], v[2 * j + 1]);
         store_packed(P, ld, n0, w, nvalid);
     }
     // same with the row already packed (w[j] = columns 2j, 2j+1): lets an epilogue with two outputs pack one of them
     // pair by pair while it computes, instead of holding 32 more floats
-    __device__ __forceinline__ void store_packed(__nv_bfloat16* P, int64_t ld, int n0, const uint32_t w[16], int nvalid) const {
+    __device__ __forceinline__ void store_packed(void* Pv, int64_t ld, int n0, const uint32_t w[16], int nvalid) const {
+        uint16_t* P = reinterpret_cast<uint16_t*>(Pv);
         const uint32_t h = slot + flip;
         flip ^= 2048u;
 #pragma unroll
@@ -307,13 +339,13 @@ struct WarpIO {
             uint4 q;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(src + (uint32_t)i * 512u) : "memory");
             if ((i * 8 + r) >= rows_left || pv <= 0) continue;
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(base + i * step);
+            uint16_t* dst = reinterpret_cast<uint16_t*>(base + i * step);
             if (pv >= 8) { *reinterpret_cast<uint4*>(dst) = q; continue; }
             uint32_t w = q.x;
 #pragma unroll 1
             for (int j = 0; j < pv; ++j) {
                 if (j == 2) w = q.y; else if (j == 4) w = q.z; else if (j == 6) w = q.w;
-                *reinterpret_cast<uint16_t*>(dst + j) = (uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu));
+                dst[j] = (uint16_t)((j & 1) ? (w >> 16) : (w & 0xffffu));
             }
         }
     }
@@ -379,7 +411,7 @@ struct WarpIO {
 // shared-memory carve-up
 // ----------------------------------------------------------------------------------------------------------
 struct Barriers {
-    uint64_t full[kMaxStages], empty[kMaxStages], bfull, tfull[2], tempty[2];
+    uint64_t full[kMaxStages], empty[kMaxStages], conv[kMaxStages], bfull, tfull[2], tempty[2];
     uint32_t tmem_base, pad;
 };
 
@@ -407,7 +439,7 @@ constexpr int kMaxChunksPerWarp = 4;   // 256 accumulator columns / 32 / 2 warps
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, int64_t M, int BN, int KB,
-          int stages, Epi epi) {
+          int stages, int a_fmt, int w_fmt, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -461,7 +493,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     } else if (warp == 1) {
         if (lane == 0) {
             // ---- MMA issuer
-            const uint32_t idesc = instr_desc(BM, BN, 0, 0);
+            const uint32_t idesc = instr_desc(BM, BN, 0, 0, a_fmt, w_fmt);
             mbar_wait(smem_u32(&bars->bfull), 0);
             int s = 0; uint32_t ph = 0; uint32_t it = 0;
             for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -565,7 +597,8 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int BJ,
-           int64_t rows_per_split, int stages, Epi epi, float* __restrict__ colsum, int colsum_n, int colsum_perm) {
+           int64_t rows_per_split, int stages, int x_fmt, int y_fmt, Epi epi, float* __restrict__ colsum, int colsum_n,
+           int colsum_perm) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -579,6 +612,10 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     const int64_t r0 = (int64_t)blockIdx.z * rows_per_split;
     const int64_t r1 = (r0 + rows_per_split < Mrows) ? r0 + rows_per_split : Mrows;
     const bool do_colsum = colsum != nullptr && blockIdx.y == 0;   // out[i] += sum_m X[m, i]: bias gradients for free
+    // mixed formats (pbar^T h, a^T t: one adjoint-like bf16 operand, one forward-like fp16 operand): the epilogue
+    // warps, idle during the main loop, round the fp16 boxes of every stage to bf16 in place before the MMAs read them
+    const bool do_conv = x_fmt != y_fmt;
+    const int mma_fmt = do_conv ? (int)kBF16 : x_fmt;
     const int nkb = r1 > r0 ? (int)((r1 - r0 + 63) / 64) : 0;   // the last block of a split may run past r1: the host
                                                                  // makes rows_per_split a multiple of 64, so only the
                                                                  // global tail is ragged and TMA zero-fills it
@@ -586,7 +623,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapY);
         // a stage is released by the MMA commit and, when the column sums of X ride along, by the 8 reducing warps
-        for (int s = 0; s < stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), do_colsum ? 1 + kEpiWarps : 1); }
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(smem_u32(&bars->full[s]), 1);
+            mbar_init(smem_u32(&bars->empty[s]), do_colsum ? 1 + kEpiWarps : 1);
+            mbar_init(smem_u32(&bars->conv[s]), kEpiWarps);
+        }
         mbar_init(smem_u32(&bars->tfull[0]), 1);
         fence_barrier_init();
     }
@@ -612,10 +653,10 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
-            const uint32_t idesc = instr_desc(128, BJ, 1, 1);
+            const uint32_t idesc = instr_desc(128, BJ, 1, 1, mma_fmt, mma_fmt);
             int s = 0; uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(smem_u32(&bars->full[s]), ph);
+                mbar_wait(smem_u32(do_conv ? &bars->conv[s] : &bars->full[s]), ph);
                 tc_fence_after();
                 const uint32_t st = base + s * stage_bytes;
 #pragma unroll
@@ -632,35 +673,60 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         }
         __syncwarp();
     } else if (nkb > 0) {
-        if (do_colsum) {
-            // While the MMAs run these 8 warps are idle: they read the X boxes of every stage out of shared memory
-            // (the operand is there anyway) and accumulate its column sums.  Thread t: column pair (t & 63) of the
-            // 128-column tile, k-rows 16 (t >> 6) .. +15 of the 64-row block; a warp reads whole 128-byte swizzle rows.
+        if (do_colsum || do_conv) {
+            // While the MMAs run these 8 warps are idle.  Per stage they (1) round the fp16 operand's boxes to bf16 in
+            // place (element-wise, so the swizzle does not matter; 16-byte vectors, thread t takes vectors t, t + 256,
+            // ...), make the writes visible to the tensor core (async proxy) and release the stage to the MMA warp;
+            // (2) read the X boxes out of shared memory (the operand is there anyway) and accumulate its column sums.
+            // Thread t: column pair (t & 63) of the 128-column tile, k-rows 16 (t >> 6) .. +15 of the 64-row block; a
+            // warp reads whole 128-byte swizzle rows.
             const int t = (int)threadIdx.x - 64;
             const int pi = t & 63, g = t >> 6;
             const int c = (pi & 31) * 2;
             const uint32_t box_off = (uint32_t)(pi >> 5) * kBox;
+            const uint32_t conv_off = x_fmt == kF16 ? 0u : nbx * kBox;
+            const int conv_vecs = (int)((x_fmt == kF16 ? nbx : nby) * (kBox / 16u));
+            const bool x_bf16 = do_conv || x_fmt == kBF16;          // format of X once the stage is released
             float s0 = 0.f, s1 = 0.f;
             int s = 0; uint32_t ph = 0;
             for (int kb = 0; kb < nkb; ++kb) {
                 if (lane == 0) mbar_wait(smem_u32(&bars->full[s]), ph);   // one poller per warp
                 __syncwarp();
-                const uint32_t st = base + s * stage_bytes + box_off;
+                if (do_conv) {
+                    const uint32_t cb = base + s * stage_bytes + conv_off;
+                    for (int i = t; i < conv_vecs; i += kEpiWarps * 32) {
+                        uint32_t w[4];
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(cb + (uint32_t)i * 16u) : "memory");
 #pragma unroll
-                for (int kk = 0; kk < 16; ++kk) {
-                    const int k = g * 16 + kk;
-                    uint32_t w;
-                    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(st + (uint32_t)(k * 128 + ((((c >> 3) ^ (k & 7)) << 4) | ((c & 7) * 2)))) : "memory");
-                    s0 += __uint_as_float(w << 16);
-                    s1 += __uint_as_float(w & 0xffff0000u);
+                        for (int j = 0; j < 4; ++j) w[j] = WarpIO::pack2<kBF16>(WarpIO::lo_of<kF16>(w[j]), WarpIO::hi_of<kF16>(w[j]));
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cb + (uint32_t)i * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->conv[s]));
+                    // X converted by OTHER warps is only read below when X is the fp16 operand, and column sums are
+                    // never requested for that call (the sweeps sum adjoint-like, i.e. bf16, matrices only)
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&bars->empty[s]));
+                if (do_colsum) {
+                    const uint32_t st = base + s * stage_bytes + box_off;
+#pragma unroll
+                    for (int kk = 0; kk < 16; ++kk) {
+                        const int k = g * 16 + kk;
+                        uint32_t w;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(st + (uint32_t)(k * 128 + ((((c >> 3) ^ (k & 7)) << 4) | ((c & 7) * 2)))) : "memory");
+                        s0 += x_bf16 ? WarpIO::lo_of<kBF16>(w) : WarpIO::lo_of<kF16>(w);
+                        s1 += x_bf16 ? WarpIO::hi_of<kBF16>(w) : WarpIO::hi_of<kF16>(w);
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(&bars->empty[s]));
+                }
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
-            const int col = i0 + (pi >> 5) * 64 + c;
-            if (col < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col == colsum_perm - 1 ? 0 : col + 1) : col), s0);
-            if (col + 1 < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col + 1 == colsum_perm - 1 ? 0 : col + 2) : col + 1), s1);
+            if (do_colsum) {
+                const int col = i0 + (pi >> 5) * 64 + c;
+                if (col < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col == colsum_perm - 1 ? 0 : col + 1) : col), s0);
+                if (col + 1 < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col + 1 == colsum_perm - 1 ? 0 : col + 2) : col + 1), s1);
+            }
         }
         const int q = warp & 3, half = (warp - 2) >> 2;
         const int chunks = (BJ + 31) / 32;
@@ -698,7 +764,7 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64 cols], 128-byte swizzle
-inline int make_map(CUtensorMap* map, const __nv_bfloat16* p, int64_t rows, int64_t cols, int64_t ld, int box_rows, const char* who) {
+inline int make_map(CUtensorMap* map, const void* p, int fmt, int64_t rows, int64_t cols, int64_t ld, int box_rows, const char* who) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { msdf_set_error("%s: cuTensorMapEncodeTiled is unavailable", who); return MSDF_ERR_CUDA; }
     if ((((uintptr_t)p) & 15) != 0 || (ld % 8) != 0) { msdf_set_error("%s: TMA operand must be 16-byte aligned (ld %% 8 == 0)", who); return MSDF_ERR_ARG; }
@@ -706,7 +772,7 @@ inline int make_map(CUtensorMap* map, const __nv_bfloat16* p, int64_t rows, int6
     cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
     cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
-    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(p), gdim, gstr, box, estr,
+    CUresult r = fn(map, fmt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p), gdim, gstr, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { msdf_set_error("%s: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", who, (int)r,
@@ -722,16 +788,17 @@ inline int sm_count() {
 
 // C = epi(A W^T): A [M, Kp] (ld lda), W [BN, Kp] (ld ldw); Kp multiple of 64 (<= 320), BN multiple of 16 (<= 256)
 template <class Epi>
-int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __nv_bfloat16* W, int64_t ldw, int BN, const Epi& epi,
+int launch_gemm(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, const void* W, int w_fmt, int64_t ldw, int BN, const Epi& epi,
                 cudaStream_t st, const char* what) {
     if (M <= 0) return MSDF_OK;
+    if (a_fmt != w_fmt) { msdf_set_error("%s: both MMA operands must have the same 16-bit format", what); return MSDF_ERR_ARG; }
     if (Kp % 64 != 0 || Kp <= 0 || Kp > 640 || BN % 16 != 0 || BN < 16 || BN > 256) {
         msdf_set_error("%s: tensor-core GEMM needs K %% 64 == 0 (<= 640) and N %% 16 == 0 (<= 256); got K=%d N=%d", what, Kp, BN);
         return MSDF_ERR_ARG;
     }
     CUtensorMap mA, mW;
-    int rc = make_map(&mA, A, M, Kp, lda, BM, what); if (rc) return rc;
-    rc = make_map(&mW, W, BN, Kp, ldw, BN, what); if (rc) return rc;
+    int rc = make_map(&mA, A, a_fmt, M, Kp, lda, BM, what); if (rc) return rc;
+    rc = make_map(&mW, W, w_fmt, BN, Kp, ldw, BN, what); if (rc) return rc;
     const int KB = Kp / 64;
     const size_t wbytes = (size_t)KB * BN * 128;
     const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes + kColVecBytes;
@@ -750,7 +817,7 @@ int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __
     // algorithmic bytes: the A tile once, plus every bf16 operand the epilogue reads back and writes (epi.N real columns)
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
                                      (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(Epi::kPre + Epi::kStores)));
-    k_tc_gemm<Epi><<<grid, kThreads, smem, st>>>(mA, mW, M, BN, KB, stages, epi);
+    k_tc_gemm<Epi><<<grid, kThreads, smem, st>>>(mA, mW, M, BN, KB, stages, a_fmt, w_fmt, epi);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
@@ -760,13 +827,17 @@ int launch_gemm(const __nv_bfloat16* A, int64_t lda, int64_t M, int Kp, const __
 // dW[i,j] (+)= sum_m X[m,i] Y[m,j]: X [M, Ci] (ld ldx), Y [M, Cj] (ld ldy), Ci / Cj = padded column counts (multiples
 // of 64); the functor masks i / j beyond the real sizes and accumulates atomically.
 template <class Epi>
-int launch_wgrad(const __nv_bfloat16* X, int64_t ldx, int Ci, const __nv_bfloat16* Y, int64_t ldy, int Cj, int64_t M, const Epi& epi,
+int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, int y_fmt, int64_t ldy, int Cj, int64_t M, const Epi& epi,
                  cudaStream_t st, const char* what, float* colsum = nullptr, int colsum_n = 0, int colsum_perm = 0) {
     if (M <= 0) return MSDF_OK;
     if (Ci % 64 != 0 || Cj % 64 != 0 || Ci <= 0 || Cj <= 0) { msdf_set_error("%s: wgrad needs column counts %% 64 == 0", what); return MSDF_ERR_ARG; }
+    if (colsum != nullptr && x_fmt != y_fmt && x_fmt == kF16) {
+        msdf_set_error("%s: column sums of the fp16 operand of a mixed-format weight gradient are not supported", what);
+        return MSDF_ERR_UNSUPPORTED;
+    }
     CUtensorMap mX, mY;
-    int rc = make_map(&mX, X, M, Ci, ldx, 64, what); if (rc) return rc;
-    rc = make_map(&mY, Y, M, Cj, ldy, 64, what); if (rc) return rc;
+    int rc = make_map(&mX, X, x_fmt, M, Ci, ldx, 64, what); if (rc) return rc;
+    rc = make_map(&mY, Y, y_fmt, M, Cj, ldy, 64, what); if (rc) return rc;
     const int BJ = Cj < 256 ? Cj : 256;
     const int it = (Ci + 127) / 128, jt = (Cj + BJ - 1) / BJ;
     int splits = (sm_count() + it * jt - 1) / (it * jt);
@@ -787,7 +858,7 @@ int launch_wgrad(const __nv_bfloat16* X, int64_t ldx, int Ci, const __nv_bfloat1
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st, (double)M * 2.0 * (double)(Ci + Cj));
-    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, epi, colsum, colsum_n, colsum_perm);
+    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);

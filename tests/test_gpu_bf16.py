@@ -31,10 +31,12 @@ def rel_l2(a, b):
 
 
 def test_tensor_core_engine_selftest():
-    """Every shape of the tcgen05 GEMM / weight-gradient kernels against a naive kernel on the same bf16 inputs."""
+    """Every shape / operand format (fp16, bf16, mixed) of the tcgen05 GEMM and weight-gradient kernels against a
+    naive kernel on the same 16-bit inputs."""
     from monosdf_b200 import _lib
     torch.zeros(1, device=DEV)
-    for v in range(10):
+    assert _lib.lib().msdf_tc_selftest_count() >= 11
+    for v in range(_lib.lib().msdf_tc_selftest_count()):
         res = (ctypes.c_float * 2)()
         rc = _lib.lib().msdf_tc_selftest(v, res, None)
         assert rc == 0, _lib.lib().msdf_last_error().decode()

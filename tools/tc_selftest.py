@@ -6,7 +6,7 @@ from monosdf_b200 import _lib
 torch.cuda.init()
 torch.zeros(1, device="cuda")
 ok = True
-for v in range(10):
+for v in range(_lib.lib().msdf_tc_selftest_count()):
     res = (ctypes.c_float * 2)()
     rc = _lib.lib().msdf_tc_selftest(v, res, None)
     if rc != 0:
