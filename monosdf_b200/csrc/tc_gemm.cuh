@@ -613,7 +613,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     const int64_t r1 = (r0 + rows_per_split < Mrows) ? r0 + rows_per_split : Mrows;
     const bool do_colsum = colsum != nullptr && blockIdx.y == 0;   // out[i] += sum_m X[m, i]: bias gradients for free
     // mixed formats (pbar^T h, a^T t: one adjoint-like bf16 operand, one forward-like fp16 operand): the epilogue
-    // warps, idle during the main loop, round the fp16 boxes of every stage to bf16 in place before the MMAs read them
+    // warps, idle during the main loop, round the fp16 boxes of every stage to bf16 in place before the MMAs read them.
+    // The kernel is bound by shared-memory bandwidth (TMA write + MMA read = 96 KB per stage; the conversion adds a
+    // read and a write of the fp16 boxes: 128 / 160 KB, measured 1.7x per launch).  Tried and rejected: the epilogue
+    // warps loading the fp16 operand with LDG two stages ahead and writing the swizzled boxes themselves (96 KB of
+    // shared-memory traffic again, but 64 KB of loads in flight per SM is more than the LSU path sustains: 2.2x).
     const bool do_conv = x_fmt != y_fmt;
     const int mma_fmt = do_conv ? (int)kBF16 : x_fmt;
     const int nkb = r1 > r0 ? (int)((r1 - r0 + 63) / 64) : 0;   // the last block of a split may run past r1: the host

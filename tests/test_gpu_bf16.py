@@ -1,12 +1,12 @@
-"""bf16 tensor-core mode (tcgen05 / TMEM / TMA GEMMs) against the fp32 oracle, tolerance 2e-2 (BASELINE.json north_star),
-and the saved-activation backward against the recomputing one.
+"""Tensor-core mode ("bf16" mode: tcgen05 / TMEM / TMA GEMMs on 16-bit operands) against the fp32 oracle, tolerance
+2e-2 (BASELINE.json north_star), and the saved-activation backward against the recomputing one.
 
-Error measure.  The network's own outputs (sdf, grad_x sdf at given points) and the parameter gradients are checked
-in the max norm (|a - b|_inf / |b|_inf < 2e-2), like the fp32 tests.  The RENDERED maps are checked in the relative L2
-norm (|a - b|_2 / |b|_2 < 2e-2) with a looser cap on the max norm: compositing divides the sdf by beta (0.01 - 0.02
-in the fixtures), so the ~3e-3 absolute sdf error that bf16 activations carry moves the weight of single samples by a
-visible amount on the few rays that graze the surface, while the image as a whole stays within 2e-2 (DESIGN.md,
-"Precision modes").
+Error measure: |a - b|_inf / |b|_inf < 2e-2 (the max norm, like the fp32 tests) for every output of the path -- the
+network's own outputs (sdf, grad_x sdf), the rendered maps, the per-sample compositing weights, the parameter gradients
+of the field for identical upstream adjoints -- and |a - b|_2 / |b|_2 < 2e-2 for the end-to-end parameter gradient of a
+training step.  Forward-like matrices are stored in fp16 ("Precision modes"): with bf16 activations the
+3e-3 absolute sdf error was a sizeable fraction of beta (0.01 - 0.02 in the fixtures) and the weights / end-to-end
+gradient missed the tolerance; measured now: sdf 5e-4, weights 1.8e-2 (max norm), end-to-end gradient 8e-3.
 """
 import ctypes
 
@@ -70,25 +70,27 @@ def test_bf16_train_step_matches_oracle(golden, case):
     out_o = port.model_forward(params, cfg, rays, torch.zeros(n, dtype=torch.long), if_pixel_input=True, training=True,
                                eik_points=model._last_eikonal_points.cpu(), z_vals=out["z_vals"].detach().cpu())
     for k in ["sdf", "grad_theta", "grad_theta_nei"]:
+        print("REPORT %s %s max-norm %.3e" % (case, k, rel_err(out[k], out_o[k])))
         assert rel_err(out[k], out_o[k]) < BF16_TOL, (k, rel_err(out[k], out_o[k]))
     for k in ["rgb_values", "depth_values", "normal_map"]:
+        print("REPORT %s %s l2 %.3e max-norm %.3e" % (case, k, rel_l2(out[k], out_o[k]), rel_err(out[k], out_o[k])))
         assert rel_l2(out[k], out_o[k]) < BF16_TOL, (k, rel_l2(out[k], out_o[k]))
-        assert rel_err(out[k], out_o[k]) < 0.15, (k, rel_err(out[k], out_o[k]))
-    # per-sample compositing weights: exp(-sdf / beta) amplifies the bf16 sdf error sample by sample (beta = 0.01-0.02
-    # here); they are an intermediate, not one of the maps the tolerance is stated for -- sanity bound only
-    assert rel_l2(out["weights"], out_o["weights"]) < 0.25
+        assert rel_err(out[k], out_o[k]) < BF16_TOL, (k, rel_err(out[k], out_o[k]))
+    print("REPORT %s weights l2 %.3e max-norm %.3e" % (case, rel_l2(out["weights"], out_o["weights"]), rel_err(out["weights"], out_o["weights"])))
+    # per-sample compositing weights: exp(-sdf / beta) amplifies the sdf error sample by sample (beta = 0.01-0.02 here)
+    assert rel_err(out["weights"], out_o["weights"]) < BF16_TOL, rel_err(out["weights"], out_o["weights"])
     loss_o = port.monosdf_loss(out_o, gt)
     assert float(loss["loss"]) == pytest.approx(float(loss_o["loss"]), rel=BF16_TOL)
-    # End-to-end parameter gradients: dL/dsdf goes through exp(-sdf / beta), so the bf16 sdf error (a fraction of beta
-    # at beta = 0.01-0.02) changes the loss gradient itself, per sample, before the field's backward even starts.  With
-    # a few dozen rays nothing averages out; the whole-gradient direction is what is asserted here, the 2e-2 bound of
-    # the field's backward for IDENTICAL upstream adjoints is test_bf16_field_backward_matches_fp32.
+    # End-to-end parameter gradients (dL/dsdf goes through exp(-sdf / beta), the field's backward through bf16
+    # adjoints): the whole gradient vector in the relative L2 norm; per-parameter bounds for IDENTICAL upstream
+    # adjoints are test_bf16_field_backward_matches_fp32.
     loss_o["loss"].backward()
     ours = torch.cat([p.grad.flatten().cpu() for k, p in model.named_parameters() if params[k].grad is not None]).double()
     ref = torch.cat([params[k].grad.flatten() for k, p in model.named_parameters() if params[k].grad is not None]).double()
     cos = float((ours * ref).sum() / (ours.norm() * ref.norm()))
-    assert cos > 0.97, cos
-    assert abs(float(ours.norm() / ref.norm()) - 1.0) < 0.1
+    print("REPORT %s e2e gradient: cosine %.6f norm ratio %.4f rel-l2 %.3e" % (case, cos, float(ours.norm() / ref.norm()), float((ours - ref).norm() / ref.norm())))
+    assert cos > 0.999, cos
+    assert float((ours - ref).norm() / ref.norm()) < BF16_TOL
 
 
 @pytest.mark.parametrize("case", ["mlp_small", "mlp_full"])
@@ -157,4 +159,5 @@ def test_bf16_eval_render_close_to_fp32(golden):
         model.set_precision("bf16")
         out = model(rays, idx, if_pixel_input=True)
     for k in ["rgb_values", "depth_values", "normal_map"]:
-        assert rel_l2(out[k], ref[k]) < BF16_TOL, (k, rel_l2(out[k], ref[k]))
+        print("REPORT eval %s l2 %.3e max-norm %.3e" % (k, rel_l2(out[k], ref[k]), rel_err(out[k], ref[k])))
+        assert rel_err(out[k], ref[k]) < BF16_TOL, (k, rel_err(out[k], ref[k]))
