@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=65536, help="rays per step PER GPU (weak scaling)")
+    ap.add_argument("--total-rays", type=int, default=0,
+                    help="strong scaling (BASELINE config 5): rays per step of the WHOLE job, split evenly over the GPUs "
+                         "(e.g. 262144); overrides --rays")
     ap.add_argument("--config", default="mlp", choices=["mlp", "grid"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"],
                     help="bf16: tcgen05 tensor-core mode (2e-2 parity, headline); fp32: SIMT mode (1e-4 parity)")
@@ -52,6 +55,9 @@ def workload_name(args):
         net = "scannet_mlp-shaped MonoSDF MLP (8x256 SDF, PE 6, 2x256 colour, PE 4), ErrorBoundSampler 64+32+2"
     else:
         net = "kitchen_HDR_grids-shaped hash grid (16x2, 2^19, 16-2048) + 2x256 SDF MLP + 2x256 colour"
+    if args.total_rays:
+        return "%s, %d synthetic rays/step over all GPUs (strong scaling), pixel-mode rays, beta=%g, MonoSDFLoss, fwd+bwd+Adam" % (
+            net, args.total_rays, args.beta)
     return "%s, %d synthetic rays/step/GPU, pixel-mode rays, beta=%g, MonoSDFLoss, fwd+bwd+Adam" % (net, args.rays, args.beta)
 
 
@@ -179,6 +185,9 @@ def run_ours(args):
     arena, opt = training.build_optimizer(model)
     loss_fn = MonoSDFLoss()
 
+    if args.total_rays:               # strong scaling: rank r renders rays [r N / W, (r + 1) N / W) of the step
+        lo, hi = training.shard_range(args.total_rays, rank, world)
+        args.rays = hi - lo
     n = args.rays
     g = torch.Generator().manual_seed(1 + rank)
     o = (torch.rand(n, 3, generator=g) - 0.5) * 0.6
@@ -265,7 +274,8 @@ def run_ours(args):
     gbs = (g_bytes / 1e9) / (g_ms / 1e3) if g_ms > 0 else 0.0
     table = GFLOP_PER_RAY_MLP if args.config == "mlp" else GFLOP_PER_RAY_GRID
     step_tf = table[min(max(rounds, 1), 5)] * 1e9 * n * args.steps / (ms / 1e3) / 1e12
-    value = world * n * args.steps / (ms / 1e3)
+    rays_per_step = args.total_rays if args.total_rays else world * n
+    value = rays_per_step * args.steps / (ms / 1e3)
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes / launch of the same kernel from ncu --set full
     if os.path.exists(tr_path):
@@ -278,14 +288,14 @@ def run_ours(args):
                             "frac": (k_bytes / 1e9) / (k_ms / 1e3) / peak_bw, "launches": int(k_n), "ms_per_step": k_ms}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.total_rays else "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_name(args), "rays_per_step_per_gpu": n, "sampler_rounds": rounds,
                    "precision_mode": args.precision, "parallelism": "ray-sharded dp%d, one NCCL all-reduce of the flat gradient arena" % world,
                    "l2_policy": "inputs larger than L2: every field chunk streams %.1f GB of activations through HBM (L2 is 126 MB)"
                                 % (min(n * 98, 262144) * 9.9e3 / 1e9)},
         "clocks": clk,
-        "e2e": {"value": world * n * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
+        "e2e": {"value": rays_per_step * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "k_gemm (fp32 SIMT MLP sweeps)" if gemm_cls == 0 else "k_tc_gemm + k_tc_wgrad (tcgen05 MLP sweeps)",
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,

@@ -25,7 +25,7 @@ extern "C" {
 #endif
 
 #define MSDF_MAX_LAYERS 12
-#define MSDF_ABI_VERSION 2
+#define MSDF_ABI_VERSION 3
 
 /* ------------------------------------------------------------------ library ------------------------------ */
 const char* msdf_last_error(void);
@@ -125,6 +125,12 @@ typedef struct {
     int32_t code_dim;                    /* 0 or 32 (per_image_code)                                        */
     int32_t code_per_ray;                /* 1: code[n_rays,code_dim] (:411-412); 0: code[1,code_dim] (:409) */
     int32_t final_act;                   /* 0 = sigmoid, 1 = relu (HDR, :465-468)                           */
+    int32_t spec;                        /* 1 = diffuse/specular split (spec=True, :427-454; HDR only): every layer
+                                          * is followed by ReLU, the first 3 outputs of layer L-3 are the diffuse
+                                          * colour, the remaining ones feed layer L-2 (in_dim = out_dim - 3), the last
+                                          * layer yields the specular colour; rgb = diffuse + specular.  The rgb
+                                          * buffers of msdf_field_forward / _backward are then [M,6] = [rgb | rgb_spec]
+                                          * (and d_rgb [M,6] = [dL/drgb | dL/drgb_spec]).                      */
 } msdf_color_desc;
 
 #define MSDF_MODE_SDF_ONLY 0   /* get_sdf_vals, network.py:131-137,307-309 (sampler, marching cubes)         */
@@ -179,6 +185,18 @@ int msdf_ray_points(const float* ray_o, const float* ray_d, const float* z, int6
  * intrinsics [B,4,4] -> ray_dirs [B,N,3] (unit), cam_loc [B,3]. */
 int msdf_camera_rays(const float* uv, const float* pose, const float* intrinsics, int64_t batch, int64_t n_pixels,
                      float* ray_dirs, float* cam_loc, void* stream);
+
+/* Pixel-mode batch assembly on the device ("next" row f3): what SceneDatasetDN.convert_to_pixels / __getitem__ /
+ * collate_fn (datasets/scene_dataset.py:269-307, 374-401, 438-464) hand the trainer, computed per sampled ray from the
+ * per-frame data.  Ray id r addresses pixel p = r % (H*W) (row p / W, column p % W, uv = (column, row), :258-260) of
+ * frame f = r / (H*W).  poses / intrinsics [n_frames,4,4]; rgb / normal [n_frames*H*W,3], depth / mask [n_frames*H*W]
+ * (any may be NULL together with its output).  Outputs for the n ids: ray_dirs, ray_dirs_tmp (identity pose), ray_cam_loc
+ * [n,3], ray_pose [n,4,4], frame_idx [n] int64 and the gathered ground-truth rows.  bad_flag: device int the caller
+ * zeroes; set to 1 when an id is out of range (that ray then reads ray 0). */
+int msdf_pixel_batch(const int64_t* ray_ids, int64_t n, const float* poses, const float* intrinsics, int64_t n_frames,
+                     int height, int width, const float* rgb, const float* depth, const float* mask, const float* normal,
+                     float* ray_dirs, float* ray_dirs_tmp, float* ray_cam_loc, float* ray_pose, int64_t* frame_idx,
+                     float* gt_rgb, float* gt_depth, float* gt_mask, float* gt_normal, int* bad_flag, void* stream);
 
 /* ------------------------------------------------------------------ compositing ---------------------------
  * LaplaceDensity (density.py:21-30) + volume_rendering (network.py:626-640) + the weighted sums and the

@@ -40,7 +40,7 @@ class LossDesc(Structure):
 
 class ColorDesc(Structure):
     _fields_ = [("mode_idr", c_int32), ("multires_view", c_int32), ("feat_dim", c_int32), ("code_dim", c_int32),
-                ("code_per_ray", c_int32), ("final_act", c_int32)]
+                ("code_per_ray", c_int32), ("final_act", c_int32), ("spec", c_int32)]
 
 
 _P = c_void_p
@@ -64,6 +64,7 @@ _SIGNATURES = {
                                     POINTER(MlpGrads), POINTER(MlpGrads), _P, _P, _P, c_size_t, _P]),
     "msdf_ray_points": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "msdf_camera_rays": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P]),
+    "msdf_pixel_batch": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "msdf_render_forward": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "msdf_render_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "msdf_weightnorm_forward": (c_int, [_P, _P, c_int, c_int, _P, c_int, _P]),
@@ -99,7 +100,7 @@ def lib():
             fn = getattr(h, name)   # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if h.msdf_abi_version() != 2:
+        if h.msdf_abi_version() != 3:
             raise RuntimeError("monosdf_b200: ABI version mismatch")
         _lib = h
     return _lib

@@ -184,6 +184,8 @@ struct Net {
     bf16* Wkb[MSDF_MAX_LAYERS]; bf16* Wtb[MSDF_MAX_LAYERS];
     const void* wk(int l, int fmt) const { return fmt == msdf_tc::kBF16 ? (const void*)Wkb[l] : (const void*)Wk[l]; }
     const void* wt(int l, int fmt) const { return fmt == msdf_tc::kBF16 ? (const void*)Wtb[l] : (const void*)Wt[l]; }
+    int tap;           // colour net, spec variant: the first 3 outputs of layer `tap` leave the chain (diffuse colour) and
+                       // layer tap + 1 takes the remaining ones; -1 otherwise
     int perm_last;     // 1: rows of the last layer are ordered [features..., sdf] in Wk/Wt (bf16 SDF net)
     int rot0;          // bf16 copies of layer 0: input column k' holds W[:, (k' + rot0) % in] (rotated colour input)
 };
@@ -191,11 +193,18 @@ struct Net {
 inline int round_up(int x, int a) { return (x + a - 1) / a * a; }
 template <class T> inline int padw(int n) { return kIsBf16<T> ? round_up(n, 64) : round_up(n, 4); }
 
-int make_net(const msdf_mlp_desc* d, Net& n, const char* who) {
+constexpr int kTapN = 3;   // diffuse colour channels tapped off the colour net (network.py:441)
+
+// row order of the 16-bit weight copies / of the matrices those layers write: the first `shift` rows moved to the end
+// (1: SDF net's last layer -> [features..., sdf]; 3: tapped colour layer -> [specular features..., diffuse])
+inline int row_shift(const Net& n, int l) { return (n.perm_last && l == n.L - 1) ? 1 : ((n.tap >= 0 && l == n.tap) ? kTapN : 0); }
+
+int make_net(const msdf_mlp_desc* d, Net& n, const char* who, int tap = -1) {
     MSDF_CHECK_ARG(d != nullptr, "%s: null network descriptor", who);
     MSDF_CHECK_ARG(d->n_layers >= 2 && d->n_layers <= MSDF_MAX_LAYERS, "%s: n_layers=%d not in [2,%d]", who, d->n_layers,
                    MSDF_MAX_LAYERS);
-    n.L = d->n_layers; n.d0 = d->d0; n.skip = d->skip_layer; n.perm_last = 0; n.rot0 = 0;
+    n.L = d->n_layers; n.d0 = d->d0; n.skip = d->skip_layer; n.perm_last = 0; n.rot0 = 0; n.tap = tap;
+    MSDF_CHECK_ARG(tap < 0 || (tap >= 1 && tap + 1 < n.L), "%s: the diffuse/specular split needs at least 4 layers", who);
     MSDF_CHECK_ARG(n.skip < n.L && n.skip != 0, "%s: skip_layer=%d invalid", who, n.skip);
     int w = 0;
     for (int l = 0; l < n.L; ++l) {
@@ -203,10 +212,11 @@ int make_net(const msdf_mlp_desc* d, Net& n, const char* who) {
         n.Wk[l] = n.Wt[l] = nullptr; n.Wkb[l] = n.Wtb[l] = nullptr;
         MSDF_CHECK_ARG(n.W[l] && n.b[l], "%s: layer %d has null weights", who, l);
         MSDF_CHECK_ARG(n.ldw[l] >= n.in[l] && n.in[l] > 0 && n.out[l] > 0, "%s: layer %d bad dims", who, l);
-        const int expect = (l == 0) ? n.d0 : (l == n.skip ? n.out[l - 1] + n.d0 : n.out[l - 1]);
+        const int expect = (l == 0) ? n.d0 : (l == n.skip ? n.out[l - 1] + n.d0 : (l == tap + 1 && tap >= 0 ? n.out[l - 1] - kTapN : n.out[l - 1]));
         MSDF_CHECK_ARG(n.in[l] == expect, "%s: layer %d in_dim=%d, expected %d", who, l, n.in[l], expect);
         if (l > 0) w = w > n.in[l] ? w : n.in[l];
         if (l < n.L - 1) w = w > n.out[l] ? w : n.out[l];
+        if (l == tap) MSDF_CHECK_ARG(n.out[l] > kTapN, "%s: tapped layer too narrow", who);
     }
     n.maxw = w;
     return MSDF_OK;
@@ -672,14 +682,14 @@ struct EpiRelu : EpiBase<EpiRelu<T>> {       // out[m,n] = relu(acc + b[n])
     }
     __device__ __forceinline__ const float* colvec() const { return bias; }
 };
-// C[row(m), n] += acc  (split-K weight gradients).  With perm_rows > 0 the GEMM's row index i addresses the
-// permuted last layer [features..., sdf]: i < perm_rows - 1 -> row i + 1, i == perm_rows - 1 -> row 0.
+// C[row(m), n] += acc  (split-K weight gradients).  With perm_rows > 0 the GEMM's row index i addresses a layer whose
+// first perm_shift rows were moved to the end (row_shift()): i -> row (i + perm_shift) % perm_rows.
 struct EpiAtomic : EpiBase<EpiAtomic> {
-    float* C; int64_t ldc; int Mrows; int perm_rows;
+    float* C; int64_t ldc; int Mrows; int perm_rows; int perm_shift;
     int col_rot;                                   // GEMM column c addresses column (c + col_rot) % N (rotated colour input)
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         if (m >= Mrows) return;
-        const int64_t r = perm_rows > 0 ? (m == perm_rows - 1 ? 0 : m + 1) : m;
+        const int64_t r = perm_rows > 0 ? (m + perm_shift) % perm_rows : m;
         float* o = C + r * ldc + n;
 #pragma unroll
         for (int j = 0; j < W; ++j)
@@ -691,7 +701,7 @@ struct EpiAtomic : EpiBase<EpiAtomic> {
         const EpiAtomic e = *this;
         io.atomic_add(v, (int64_t)Mrows, [=](int64_t m, int c) -> float* {
             if (c >= nv) return nullptr;
-            const int64_t r = e.perm_rows > 0 ? (m == e.perm_rows - 1 ? 0 : m + 1) : m;
+            const int64_t r = e.perm_rows > 0 ? (m + e.perm_shift) % e.perm_rows : m;
             int col = n0 + c + e.col_rot;
             if (col >= e.N) col -= e.N;
             return e.C + r * e.ldc + col;
@@ -962,6 +972,40 @@ k_head_dpre(const float* __restrict__ d_out, const float* __restrict__ out, int6
     }
 }
 
+// Diffuse/specular split (network.py:441-453).  Forward: the diffuse colour is the tapped layer's (ReLU'd) columns
+// [tap0, tap0 + 3); rgb6[m] = [diffuse + specular | specular].
+template <class TF>
+__global__ void k_spec_combine(const TF* __restrict__ Ctap, int64_t ldc, int tap0, const float* __restrict__ spec, int64_t M,
+                               float* __restrict__ rgb6) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * kTapN) return;
+    const int64_t m = i / kTapN; const int j = (int)(i - m * kTapN);
+    const float sp = spec[i];
+    rgb6[m * 6 + j] = ldf(Ctap + m * ldc + tap0 + j) + sp;
+    rgb6[m * 6 + 3 + j] = sp;
+}
+// Backward, head side: the specular head sees dL/drgb + dL/drgb_spec; its output drives act'.
+__global__ void k_spec_head_adjoint(const float* __restrict__ rgb6, const float* __restrict__ d_rgb6, int64_t M,
+                                    float* __restrict__ spec, float* __restrict__ d_spec) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * kTapN) return;
+    const int64_t m = i / kTapN; const int j = (int)(i - m * kTapN);
+    spec[i] = rgb6[m * 6 + 3 + j];
+    d_spec[i] = d_rgb6[m * 6 + j] + d_rgb6[m * 6 + 3 + j];
+}
+// Backward, tap side: adjoint of the tapped layer's pre-activation in the diffuse columns, P[m, tap0 + j] =
+// dL/drgb[m, j] * [diffuse > 0]; columns [zero_lo, zero_hi) (the K padding of the tensor-core operand) are zeroed.
+template <class TF, class T>
+__global__ void k_spec_tail(const TF* __restrict__ Ctap, int64_t ldc, int tap0, const float* __restrict__ d_rgb6, int64_t M,
+                            T* __restrict__ P, int64_t ldp, int zero_lo, int zero_hi) {
+    const int w = kTapN + (zero_hi > zero_lo ? zero_hi - zero_lo : 0);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * w) return;
+    const int64_t m = i / w; const int j = (int)(i - m * w);
+    if (j < kTapN) stf(P + m * ldp + tap0 + j, ldf(Ctap + m * ldc + tap0 + j) > 0.f ? d_rgb6[m * 6 + j] : 0.f);
+    else stf(P + m * ldp + zero_lo + (j - kTapN), 0.f);
+}
+
 // reverse-sweep start: a_{L-1} = e_0, so (a W_{L-1})[m,n] = W_{L-1}[0,n] for every point
 template <class T>
 __global__ void k_rev_init(const float* __restrict__ w_row, int64_t M, int N, EpiRev<T> epi) {
@@ -1027,8 +1071,9 @@ __global__ void k_code_grad(const float* __restrict__ dcode, int64_t n_rays, int
     out[i] += s;
 }
 
-// bf16 weight preparation for the tensor-core path.  Wk[r, k] = W[row(r), k] (zero padded to [rows_p, in_p]),
-// Wt[k, r] = W[row(r), k] (zero padded to [in_p16, rows_p64]); row(r) applies the [features..., sdf] permutation.
+// 16-bit weight preparation for the tensor-core path.  Wk[r, k] = W[row(r), k] (zero padded to [rows_p, in_p]),
+// Wt[k, r] = W[row(r), k] (zero padded to [in_p16, rows_p64]); row(r) = (r + perm) % out moves the first perm rows to
+// the end (row_shift()).
 __global__ void k_prep_weights(const float* __restrict__ W, int64_t ldw, int out, int in, int perm, int rot, Fw<bf16>* __restrict__ Wk,
                                int wk_rows, int wk_ld, Fw<bf16>* __restrict__ Wt, int wt_rows, int wt_ld, bf16* __restrict__ Wkb,
                                bf16* __restrict__ Wtb) {
@@ -1037,13 +1082,13 @@ __global__ void k_prep_weights(const float* __restrict__ W, int64_t ldw, int out
     if (i < nk) {
         const int r = (int)(i / wk_ld), k = (int)(i - (int64_t)r * wk_ld);
         float v = 0.f;
-        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + (k + rot) % in]; }
+        if (r < out && k < in) { const int src = (r + perm) % out; v = W[(int64_t)src * ldw + (k + rot) % in]; }
         stf(Wk + i, v); stf(Wkb + i, v);
     } else if (i < nk + nt) {
         const int64_t t = i - nk;
         const int k = (int)(t / wt_ld), r = (int)(t - (int64_t)k * wt_ld);
         float v = 0.f;
-        if (r < out && k < in) { const int src = perm ? (r == out - 1 ? 0 : r + 1) : r; v = W[(int64_t)src * ldw + (k + rot) % in]; }
+        if (r < out && k < in) { const int src = (r + perm) % out; v = W[(int64_t)src * ldw + (k + rot) % in]; }
         stf(Wt + t, v); stf(Wtb + t, v);
     }
 }
@@ -1074,6 +1119,7 @@ struct Bufs {
     TF* A[MSDF_MAX_LAYERS];  // a_l (forward format), later z_l / pbar_l in the adjoint format T, in place  (l < L-1)
     T *TG0, *T2[2], *Dout;
     float *G0, *BH0, *dydx, *hashf, *sdf_raw, *mask, *dn, *dn_color, *gradc, *sdfc, *dcode;
+    float *spec32, *dspec32;   // spec variant: specular head output / its adjoint, [Mc, 3]
     TF* X; TF* C[MSDF_MAX_LAYERS]; T* dC[2]; T* Hd;   // Hd: colour head dpre, [Mc, 64] (bf16 mode)
     T* adj(int l) const { return reinterpret_cast<T*>(A[l]); }   // A[l] once it holds z_l / pbar_l
     int64_t d0p, ldh, ldo, ldx, ldc;   // leading dimensions
@@ -1155,6 +1201,7 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
             b.X = p.take<TF>(Mc, b.ldx);
             b.C[0] = b.X;
             for (int l = 1; l < cx.cn.L; ++l) b.C[l] = p.take<TF>(Mc, b.ldc);
+            if (cx.cn.tap >= 0) { b.spec32 = c.take<float>(Mc, kTapN); b.dspec32 = c.take<float>(Mc, kTapN); }
             if (mode == MSDF_MODE_BACKWARD) {
                 b.dC[0] = c.take<T>(Mc, b.ldc); b.dC[1] = c.take<T>(Mc, b.ldc);
                 if (kIsBf16<T>) b.Hd = c.take<T>(Mc, 64);
@@ -1211,19 +1258,21 @@ int gemm_nt(const Ctx& c, const Net& n, int l, const TA* A, int64_t lda, int64_t
         constexpr int fa = Fmt16<TA>::value;
         const uint16_t* wk = reinterpret_cast<const uint16_t*>(n.wk(l, fa));
         const int kp = round_up(n.in[l], 64);
-        if (kp > 320) {
+        if (kp > 320 || nrows > 256) {
             // a wide first layer (e.g. 321 colour inputs with the per-image code): its weights only fit in shared
-            // memory 128 rows at a time, so the layer runs as column blocks of the output
+            // memory 128 rows at a time, so the layer runs as column blocks of the output; likewise a layer with more
+            // than 256 outputs (the 259-wide tapped layer of the spec colour net) exceeds one accumulator
+            const int blk = kp > 320 ? 128 : 256;
             if constexpr (std::is_same<Epi, EpiRelu<T>>::value || std::is_same<Epi, EpiFwdAct<T>>::value || std::is_same<Epi, EpiBias<T>>::value) {
-                for (int q0 = 0; q0 < nrows; q0 += 128) {
-                    const int nb = nrows - q0 < 128 ? nrows - q0 : 128;
+                for (int q0 = 0; q0 < nrows; q0 += blk) {
+                    const int nb = nrows - q0 < blk ? nrows - q0 : blk;
                     Epi e = epi;
                     e.N = nb; e.bias = epi.bias + q0; e.out = epi.out + q0;
                     RUN(msdf_tc::launch_gemm(A, fa, lda, Mc, kp, wk + (int64_t)(r0 + q0) * kp, fa, kp, round_up(nb, 16), e, c.st, what));
                 }
                 return MSDF_OK;
             } else {
-                msdf_set_error("%s: more than 320 input columns with this epilogue", what);
+                msdf_set_error("%s: more than 320 input / 256 output columns with this epilogue", what);
                 return MSDF_ERR_UNSUPPORTED;
             }
         }
@@ -1261,12 +1310,12 @@ int colsum(const Ctx& c, const T* X, int64_t ldx, const T* w, int64_t ws, int64_
 // gradient: in bf16 mode it rides along in the weight-gradient kernel, which has X in shared memory anyway)
 template <class T, class TX, class TY>
 int wgrad(const Ctx& c, const TX* X, int64_t ldx, const TY* Y, int64_t ldy, int rows, int cols, int64_t Mc, float* dW, int64_t ldw,
-          int perm_rows, int col_rot = 0, float* db = nullptr) {
+          int perm_rows, int col_rot = 0, float* db = nullptr, int perm_shift = 1) {
     EpiAtomic e{};
-    e.N = cols; e.C = dW; e.ldc = ldw; e.Mrows = rows; e.perm_rows = perm_rows; e.col_rot = col_rot;
+    e.N = cols; e.C = dW; e.ldc = ldw; e.Mrows = rows; e.perm_rows = perm_rows; e.perm_shift = perm_shift; e.col_rot = col_rot;
     if constexpr (kIsBf16<T>) {
         return msdf_tc::launch_wgrad(X, Fmt16<TX>::value, ldx, round_up(rows, 64), Y, Fmt16<TY>::value, ldy, round_up(cols, 64), Mc, e, c.st,
-                                     "weight gradient", db, rows, perm_rows);
+                                     "weight gradient", db, rows, perm_rows, perm_shift);
     } else {
         if (db != nullptr) {
             if (perm_rows > 0) { msdf_set_error("weight gradient: permuted bias sums are a bf16-mode feature"); return MSDF_ERR_UNSUPPORTED; }
@@ -1290,7 +1339,7 @@ int colsum(const Ctx& c, const T* X, int64_t ldx, const T* w, int64_t ws, int64_
 int prep_weights(const Ctx& c, Net& n, int perm_last) {
     n.perm_last = perm_last;
     for (int l = 0; l < n.L; ++l) {
-        const int perm = (perm_last && l == n.L - 1) ? 1 : 0;
+        const int perm = row_shift(n, l);
         const int wk_rows = round_up(n.out[l], 16), wk_ld = round_up(n.in[l], 64);
         const int wt_rows = round_up(n.in[l], 16), wt_ld = round_up(n.out[l], 64);
         const int64_t total = (int64_t)wk_rows * wk_ld + (int64_t)wt_rows * wt_ld;
@@ -1413,23 +1462,46 @@ int color_forward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, co
                                                            c.cd->code_dim, c.cd->code_per_ray, b.X, b.ldx, pad, n.rot0);
     }
     LAUNCHED("colour input");
+    // spec variant: the tapped layer's output is stored [specular features | diffuse] in tensor-core mode (rows moved
+    // by the weight copy, so the next layer's operand starts 16-byte aligned) and in the reference's order
+    // [diffuse | features] in fp32 mode; tap_in = first column of the next layer's input, tap0 = first diffuse column
+    const bool spec = n.tap >= 0;
+    const int tap_in = spec && !kIsBf16<T> ? kTapN : 0;
+    const int tap0 = spec ? (kIsBf16<T> ? n.out[n.tap] - kTapN : 0) : 0;
     for (int l = 0; l < n.L - 1; ++l) {
         EpiRelu<T> e{};
         e.bias = n.b[l]; e.out = b.C[l + 1]; e.ldo = b.ldc;
-        RUN((gemm_nt<T>(c, n, l, b.C[l], l == 0 ? b.ldx : b.ldc, Mc, 0, n.out[l], e, "colour layer")));
+        const Fw<T>* in = b.C[l] + (spec && l == n.tap + 1 ? tap_in : 0);
+        const int64_t ldin = l == 0 ? b.ldx : b.ldc;
+        if (kIsBf16<T> && spec && l == n.tap) {
+            // rows of the 16-bit copy: [features (out - 3) | diffuse (3)]; the bias vector is in the reference's order
+            const int nf = n.out[l] - kTapN;
+            e.bias = n.b[l] + kTapN;
+            RUN((gemm_nt<T>(c, n, l, in, ldin, Mc, 0, nf, e, "colour layer (specular features)")));
+            e.bias = n.b[l]; e.out = b.C[l + 1] + nf;
+            RUN((gemm_nt<T>(c, n, l, in, ldin, Mc, nf, kTapN, e, "colour layer (diffuse)")));
+            continue;
+        }
+        RUN((gemm_nt<T>(c, n, l, in, ldin, Mc, 0, n.out[l], e, "colour layer")));
     }
     const int l = n.L - 1;
     MSDF_CHECK_ARG(n.out[l] <= 4, "colour net: d_out=%d > 4 unsupported", n.out[l]);
+    MSDF_CHECK_ARG(!spec || n.out[l] == kTapN, "colour net: the diffuse/specular split needs d_out = 3");
     if (rgb == nullptr) return MSDF_OK;   // backward recompute: the saved rgb drives act', the head is not needed
+    const int act = (spec || c.cd->final_act != 0) ? kActRelu : kActSigmoid;
+    float* head_out = spec ? b.spec32 : rgb;
     if constexpr (kIsBf16<T>) {
         EpiHead e{};
-        e.bias = n.b[l]; e.out = rgb; e.ldo = n.out[l]; e.act = c.cd->final_act == 0 ? kActSigmoid : kActRelu;
+        e.bias = n.b[l]; e.out = head_out; e.ldo = n.out[l]; e.act = act;
         RUN((gemm_nt<T>(c, n, l, b.C[l], b.ldc, Mc, 0, n.out[l], e, "colour head")));
-        return MSDF_OK;
+    } else {
+        k_rowdot<4, Fw<T>><<<nblk(Mc, 8), 256, 0, c.st>>>(b.C[l], b.ldc, n.W[l], n.ldw[l], n.b[l], Mc, n.out[l], n.in[l], act, head_out, n.out[l]);
+        LAUNCHED("colour head");
     }
-    k_rowdot<4, Fw<T>><<<nblk(Mc, 8), 256, 0, c.st>>>(b.C[l], b.ldc, n.W[l], n.ldw[l], n.b[l], Mc, n.out[l], n.in[l],
-                                                 c.cd->final_act == 0 ? kActSigmoid : kActRelu, rgb, n.out[l]);
-    LAUNCHED("colour head");
+    if (spec) {
+        k_spec_combine<Fw<T>><<<nblk(Mc * kTapN), 256, 0, c.st>>>(b.C[n.tap + 1], b.ldc, tap0, b.spec32, Mc, rgb);
+        LAUNCHED("diffuse + specular");
+    }
     return MSDF_OK;
 }
 
@@ -1438,7 +1510,16 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
     const Net& n = c.cn;
     const ColorGeom& g = c.cg;
     int l = n.L - 1;
-    const int act = c.cd->final_act == 0 ? kActSigmoid : kActRelu;
+    const bool spec = n.tap >= 0;
+    const int tap_in = spec && !kIsBf16<T> ? kTapN : 0;
+    const int tap0 = spec ? (kIsBf16<T> ? n.out[n.tap] - kTapN : 0) : 0;
+    const int act = (spec || c.cd->final_act != 0) ? kActRelu : kActSigmoid;
+    const float* d_rgb6 = d_rgb;
+    if (spec) {   // rgb / d_rgb are [Mc, 6] = [rgb | rgb_spec]: the head is the specular branch
+        k_spec_head_adjoint<<<nblk(Mc * kTapN), 256, 0, c.st>>>(rgb, d_rgb, Mc, b.spec32, b.dspec32);
+        LAUNCHED("specular head adjoint");
+        rgb = b.spec32; d_rgb = b.dspec32;
+    }
     T* P = b.dC[0];
     if constexpr (kIsBf16<T>) {
         // the 3-wide head as zero-padded tensor-core GEMMs: dpre [Mc, 64] is the operand of its wgrad and dgrad
@@ -1459,12 +1540,23 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
     int pp = 0;
     for (l = n.L - 2; l >= 0; --l) {
         const int64_t ldin = l == 0 ? b.ldx : b.ldc;
-        RUN(wgrad<T>(c, P, b.ldc, b.C[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, l == 0 ? n.rot0 : 0, gr->db[l]));
+        const int in_off = spec && l == n.tap + 1 ? tap_in : 0;          // this layer reads past the diffuse columns
+        const int shift = kIsBf16<T> ? row_shift(n, l) : 0;              // rows of the tapped layer are moved in the 16-bit copies
+        RUN(wgrad<T>(c, P, b.ldc, b.C[l] + in_off, ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], shift > 0 ? n.out[l] : 0,
+                     l == 0 ? n.rot0 : 0, gr->db[l], shift > 0 ? shift : 1));
         if (l > 0) {
             T* Pn = b.dC[pp ^ 1];
             EpiBwdRelu<T> e{};
-            e.Hin = b.C[l]; e.ldh = b.ldc; e.out = Pn; e.ldo = b.ldc;
+            e.Hin = b.C[l] + in_off; e.ldh = b.ldc; e.out = Pn + in_off; e.ldo = b.ldc;
             RUN((gemm_nn<T>(c, n, l, P, b.ldc, Mc, e, "colour dgrad")));
+            if (spec && l == n.tap + 1) {
+                // Pn is now the adjoint of the tapped layer's pre-activation in the feature columns: add the diffuse
+                // columns and, in tensor-core mode, zero the K padding the next GEMMs read
+                const int no = n.out[n.tap];
+                k_spec_tail<Fw<T>, T><<<nblk(Mc * (kTapN + 64)), 256, 0, c.st>>>(b.C[l], b.ldc, tap0, d_rgb6, Mc, Pn, b.ldc, no,
+                                                                             kIsBf16<T> ? round_up(no, 64) : no);
+                LAUNCHED("diffuse adjoint");
+            }
             P = Pn; pp ^= 1;
         } else {
             EpiColorIn<T> e{};
@@ -1559,7 +1651,7 @@ int make_ctx(Ctx& c, const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc
     c.cd = cd;
     if (c.has_color) {
         MSDF_CHECK_ARG(cd != nullptr, "%s: colour descriptor missing", who);
-        RUN(make_net(color_net, c.cn, who));
+        RUN(make_net(color_net, c.cn, who, cd->spec ? color_net->n_layers - 3 : -1));
         c.cg = color_geom(cd);
         MSDF_CHECK_ARG(c.cn.skip < 0, "%s: colour net has no skip connection", who);
         MSDF_CHECK_ARG(c.cg.in0 == c.cn.d0, "%s: colour net d0=%d but inputs total %d", who, c.cn.d0, c.cg.in0);
@@ -1628,7 +1720,7 @@ int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int
             const int64_t ray0 = m0 / n_samples;
             RUN(color_forward<T>(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,
                                  code ? code + (c.cd->code_per_ray ? ray0 * c.cd->code_dim : 0) : nullptr, grad + 3 * m0,
-                                 rgb + (int64_t)c.cn.out[c.cn.L - 1] * m0));
+                                 rgb + (int64_t)(c.cn.tap >= 0 ? 2 * kTapN : c.cn.out[c.cn.L - 1]) * m0));
         }
     }
     return MSDF_OK;
@@ -1685,7 +1777,7 @@ int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, in
         }
         if (c.has_color) {
             const int64_t ray0 = m0 / n_samples;
-            const int no = c.cn.out[c.cn.L - 1];
+            const int no = c.cn.tap >= 0 ? 2 * kTapN : c.cn.out[c.cn.L - 1];   // spec: [rgb | rgb_spec]
             const msdf_color_desc* cd = c.cd;
             if (!have_saved)
                 RUN(color_forward<T>(c, b, xc, Mc, view_dirs + 3 * ray0, n_samples,

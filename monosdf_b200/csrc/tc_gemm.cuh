@@ -598,7 +598,7 @@ template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int BJ,
            int64_t rows_per_split, int stages, int x_fmt, int y_fmt, Epi epi, float* __restrict__ colsum, int colsum_n,
-           int colsum_perm) {
+           int colsum_perm, int colsum_shift) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -728,8 +728,9 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             }
             if (do_colsum) {
                 const int col = i0 + (pi >> 5) * 64 + c;
-                if (col < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col == colsum_perm - 1 ? 0 : col + 1) : col), s0);
-                if (col + 1 < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col + 1 == colsum_perm - 1 ? 0 : col + 2) : col + 1), s1);
+                // colsum_perm > 0: X's columns are a layer's rows with the first colsum_shift moved to the end
+                if (col < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col + colsum_shift) % colsum_perm : col), s0);
+                if (col + 1 < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col + 1 + colsum_shift) % colsum_perm : col + 1), s1);
             }
         }
         const int q = warp & 3, half = (warp - 2) >> 2;
@@ -832,7 +833,7 @@ int launch_gemm(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, const 
 // of 64); the functor masks i / j beyond the real sizes and accumulates atomically.
 template <class Epi>
 int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, int y_fmt, int64_t ldy, int Cj, int64_t M, const Epi& epi,
-                 cudaStream_t st, const char* what, float* colsum = nullptr, int colsum_n = 0, int colsum_perm = 0) {
+                 cudaStream_t st, const char* what, float* colsum = nullptr, int colsum_n = 0, int colsum_perm = 0, int colsum_shift = 1) {
     if (M <= 0) return MSDF_OK;
     if (Ci % 64 != 0 || Cj % 64 != 0 || Ci <= 0 || Cj <= 0) { msdf_set_error("%s: wgrad needs column counts %% 64 == 0", what); return MSDF_ERR_ARG; }
     if (colsum != nullptr && x_fmt != y_fmt && x_fmt == kF16) {
@@ -862,7 +863,7 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st, (double)M * 2.0 * (double)(Ci + Cj));
-    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm);
+    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);

@@ -142,6 +142,7 @@ class _FieldSpec:
         c.multires_view, c.feat_dim = self.color["multires_view"], self.color["feat_dim"]
         c.code_dim, c.code_per_ray = self.color["code_dim"], int(code_per_ray)
         c.final_act = 1 if self.color["hdr"] else 0
+        c.spec = 1 if self.color.get("spec") else 0
         return c
 
 
@@ -182,7 +183,9 @@ class _Field(Function):
         sdf = torch.empty(M, 1, device=dev) if kind != "gradient" else None
         grad = torch.empty(M, 3, device=dev) if kind in ("outputs", "gradient", "render") else None
         feat = torch.empty(M, F_dim, device=dev) if kind in ("forward", "outputs") else None
-        rgb = torch.empty(M, spec.color_spec.out_dims[-1], device=dev) if use_color else None
+        # spec variant: [rgb | rgb_spec] per point (include/monosdf_b200.h, msdf_color_desc.spec)
+        n_rgb = 6 if (use_color and spec.color.get("spec")) else (spec.color_spec.out_dims[-1] if use_color else 0)
+        rgb = torch.empty(M, n_rgb, device=dev) if use_color else None
         if use_color:
             view_dirs = view_dirs.contiguous().float()
             code = code.contiguous().float() if code is not None else None
@@ -475,8 +478,6 @@ class RenderingNetwork(nn.Module):
     def __init__(self, feature_vector_size, mode, d_in, d_out, dims, weight_norm=True, multires_view=0,
                  per_image_code=False, if_hdr=False, spec=False, debug=False):
         super().__init__()
-        if spec:
-            raise NotImplementedError("monosdf_b200: the diffuse/specular split (spec=True) is not built yet")
         if mode not in ("idr", "nerf"):
             raise NotImplementedError(mode)
         self.mode, self.debug, self.spec = mode, debug, spec
@@ -493,15 +494,24 @@ class RenderingNetwork(nn.Module):
             dims[0] += 32
         self.num_layers = len(dims)
         self.if_hdr = if_hdr
+        in_dims = list(dims[:-1])
+        if spec:
+            # diffuse/specular split (network.py:376-380, 427-454): the first 3 outputs of layer num_layers-4 are the
+            # diffuse colour, the rest feeds layer num_layers-3; every layer is followed by ReLU (HDR only)
+            assert if_hdr, "spec=True is an HDR-only variant (network.py:428)"
+            assert self.num_layers >= 5 and d_out == 3, "spec=True needs at least 4 linear layers and d_out = 3"
+            in_dims[self.num_layers - 3] -= 3
         for l in range(self.num_layers - 1):
             lin = nn.Linear(dims[l], dims[l + 1])
+            if in_dims[l] != dims[l]:      # the reference builds the full-width layer first and then replaces it
+                lin = nn.Linear(in_dims[l], dims[l + 1])   # (network.py:375-380): same draws from torch's RNG
             if weight_norm:
                 lin = nn.utils.weight_norm(lin)
             setattr(self, "lin" + str(l), lin)
         self.relu, self.sigmoid = nn.ReLU(), nn.Sigmoid()
-        self._net_spec = _NetSpec(dims[:-1], dims[1:], dims[0], -1)
+        self._net_spec = _NetSpec(in_dims, dims[1:], dims[0], -1)
         self._color_cfg = dict(mode=mode, multires_view=multires_view, feat_dim=feature_vector_size,
-                               code_dim=32 if per_image_code else 0, hdr=bool(if_hdr))
+                               code_dim=32 if per_image_code else 0, hdr=bool(if_hdr), spec=bool(spec))
         self._cached = None
 
     def _flat_weights(self):
@@ -602,6 +612,9 @@ class MonoSDFNetwork(nn.Module):
             sdf, grad, _, rgb_flat = _Field.apply(self._render_spec, "render", clamp, inet.sphere_scale, S, points, ray_dirs,
                                                   code, table, offsets, *inet._flat_weights(),
                                                   *self.rendering_network._flat_weights())
+            rgb_spec = None
+            if self.spec:      # [rgb | rgb_spec] per point (network.py:441-453)
+                rgb_flat, rgb_spec = rgb_flat[:, :3].contiguous(), rgb_flat[:, 3:].reshape(-1, S, 3)
             if if_pixel_input:
                 pose, pose_per_ray = input["ray_pose"], 1
             else:
@@ -618,6 +631,9 @@ class MonoSDFNetwork(nn.Module):
                 "sdf": sdf.reshape(z_vals.shape),
                 "weights": weights,
             }
+            if self.spec:      # network.py:576-582 (auxiliary output of the archived variant: plain torch on our weights)
+                output["rgb_spec"] = rgb_spec
+                output["rgb_spec_values"] = torch.sum(weights.unsqueeze(-1) * rgb_spec, 1)
             if self.training:
                 n_eik = batch_size * num_pixels
                 R = self.scene_bounding_sphere

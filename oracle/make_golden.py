@@ -30,24 +30,33 @@ GRIDMLP_CONF["Grid_MLP"] = True
 GRIDMLP_CONF["implicit_network"].update(use_grid_feature=False, divide_factor=1.1, num_levels=4, level_dim=2,
                                         base_size=4, end_size=32, logmap=10)
 
+# RenderingNetwork(spec=True): diffuse/specular split after layer 2, HDR only (network.py:376-380, 427-454; dims as in
+# confs/archive/kitchen_hdr_est_grids_spec.conf:106)
+SPEC_SMALL_CONF = copy.deepcopy(SMALL_CONF)
+SPEC_SMALL_CONF["rendering_network"].update(dims=[64, 64, 67, 64], spec=True)
+SPEC_FULL_CONF = copy.deepcopy(ref_shim.MLP_CONF)
+SPEC_FULL_CONF["rendering_network"].update(dims=[256, 256, 259, 256], spec=True)
+
 CASES = {
-    # name: (conf, n_rays, beta, store_full_grads)
+    # name: (conf, n_rays, beta, store_full_grads[, if_hdr])
     "mlp_full": (ref_shim.MLP_CONF, 24, 0.01, False),
     "mlp_small": (SMALL_CONF, 48, 0.02, True),
     "gridmlp_small": (GRIDMLP_CONF, 32, 0.02, True),
+    "spec_small": (SPEC_SMALL_CONF, 40, 0.02, True, True),
+    "spec_full": (SPEC_FULL_CONF, 16, 0.01, False, True),
 }
 
 
-def run_case(name, conf, n_rays, beta, full_grads, seed=0):
+def run_case(name, conf, n_rays, beta, full_grads, if_hdr=False, seed=0):
     net = ref_shim.load_reference()
     torch.manual_seed(seed)
-    model = net.MonoSDFNetwork(conf=ref_shim.to_conf(conf))
+    model = net.MonoSDFNetwork(conf=ref_shim.to_conf(conf), if_hdr=if_hdr)
     with torch.no_grad():
         model.density.beta.fill_(beta)
     rays = port.synthetic_rays(n_rays, seed=1)
     gt = port.synthetic_gt(n_rays, seed=2)
     indices = torch.zeros(n_rays, dtype=torch.long)
-    fx = dict(name=name, conf=conf, seed=seed, beta=beta, n_rays=n_rays)
+    fx = dict(name=name, conf=conf, seed=seed, beta=beta, n_rays=n_rays, if_hdr=if_hdr)
     # ---- eval mode (deterministic sampling)
     model.eval()
     out = model({k: v.clone() for k, v in rays.items()}, indices, if_pixel_input=True)
@@ -71,6 +80,8 @@ def run_case(name, conf, n_rays, beta, full_grads, seed=0):
     torch.manual_seed(1234)
     out = model({k: v.clone() for k, v in rays.items()}, indices, if_pixel_input=True)
     loss = port.monosdf_loss(out, gt)
+    if "rgb_spec_values" in out:    # give the specular output a gradient of its own (MonoSDFLoss does not read it)
+        loss["loss"] = loss["loss"] + 0.25 * (out["rgb_spec_values"] * gt["rgb"].reshape(-1, 3)).mean()
     model.zero_grad()
     loss["loss"].backward()
     fx["train_seed"] = 1234
@@ -90,5 +101,7 @@ def run_case(name, conf, n_rays, beta, full_grads, seed=0):
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    for name, (conf, n, beta, full) in CASES.items():
-        run_case(name, conf, n, beta, full)
+    only = sys.argv[1:]            # e.g. `python oracle/make_golden.py spec_small spec_full`: leave the others untouched
+    for name, case in CASES.items():
+        if not only or name in only:
+            run_case(name, *case)

@@ -630,6 +630,33 @@ def model_forward(params: Dict[str, Tensor], cfg: ModelCfg, inp: Dict[str, Tenso
 
 
 # --------------------------------------------------------------------------------------
+# pixel-mode data path: SceneDatasetDN.convert_to_pixels + __getitem__ + collate_fn
+# (datasets/scene_dataset.py:258-260, 269-307, 374-401, 438-464)
+# --------------------------------------------------------------------------------------
+def pixel_bank(poses: Tensor, intrinsics: Tensor, H: int, W: int) -> Dict[str, Tensor]:
+    """The per-ray arrays convert_to_pixels materialises for F frames of H x W pixels (all frames selected)."""
+    uv = np.mgrid[0:H, 0:W].astype(np.int32)                                   # :258
+    uv = torch.from_numpy(np.flip(uv, axis=0).copy()).float()                  # :259  (x = column, y = row)
+    uv = uv.reshape(2, -1).transpose(1, 0)                                     # :260  (HW, 2)
+    F_ = poses.shape[0]
+    uv_all = uv.unsqueeze(0).expand(F_, -1, -1)
+    ray_dirs, cam_loc = camera_rays(uv_all, poses, intrinsics)                 # :283
+    ray_dirs_tmp, _ = camera_rays(uv_all, torch.eye(4)[None].expand(F_, -1, -1), intrinsics)   # :288
+    hw = H * W
+    return {"ray_dirs": ray_dirs.reshape(-1, 3), "ray_dirs_tmp": ray_dirs_tmp.reshape(-1, 3),
+            "ray_cam_loc": cam_loc.unsqueeze(1).expand(-1, hw, -1).reshape(-1, 3),
+            "ray_pose": poses.unsqueeze(1).expand(-1, hw, -1, -1).reshape(-1, 4, 4),
+            "ray_frame_idx": torch.arange(F_).reshape(-1, 1).expand(-1, hw).flatten()}     # :305
+
+
+def pixel_batch(bank: Dict[str, Tensor], images: Dict[str, Tensor], ray_ids: Tensor):
+    """__getitem__ for every id + collate_fn (torch.stack / LongTensor): (indices, model_input, ground_truth)."""
+    inp = {k: bank[k][ray_ids] for k in ("ray_dirs", "ray_dirs_tmp", "ray_cam_loc", "ray_pose")}
+    gt = {k: v.reshape(-1, v.shape[-1])[ray_ids] for k, v in images.items()}
+    return bank["ray_frame_idx"][ray_ids].long(), inp, gt
+
+
+# --------------------------------------------------------------------------------------
 # MonoSDFLoss (loss.py:29-49, 75-86, 180-311) in pixel mode -- the consumer right after the path
 # --------------------------------------------------------------------------------------
 def monosdf_loss(out: Dict[str, Tensor], gt: Dict[str, Tensor], w=None) -> Dict[str, Tensor]:

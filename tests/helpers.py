@@ -9,7 +9,7 @@ def build_model(fx, device="cpu"):
     """monosdf_b200 model for a golden fixture: constructor under the fixture's seed, beta set like make_golden."""
     from monosdf_b200.model.network import MonoSDFNetwork
     torch.manual_seed(fx["seed"])
-    model = MonoSDFNetwork(to_conf(fx["conf"]))
+    model = MonoSDFNetwork(to_conf(fx["conf"]), if_hdr=fx.get("if_hdr", False))
     with torch.no_grad():
         model.density.beta.fill_(fx["beta"])
     return model.to(device)
@@ -36,7 +36,7 @@ def frac_within(a, b, tol):
 
 
 def oracle_forward(fx, params, rays, training, seed=None, eik_points=None, uv=False):
-    cfg = port.cfg_from_conf(fx["conf"])
+    cfg = port.cfg_from_conf(fx["conf"], fx.get("if_hdr", False))
     if seed is not None:
         torch.manual_seed(seed)
     n = rays["uv"].shape[1] if uv else rays["ray_dirs"].shape[0]

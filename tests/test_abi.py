@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     h = ctypes.CDLL(_lib.LIB_PATH)
     for name in _declared():
         assert hasattr(h, name), "libmonosdf_b200.so does not export %s" % name
-    assert h.msdf_abi_version() == 2
+    assert h.msdf_abi_version() == 3
 
 
 def test_binding_covers_the_header():
