@@ -198,6 +198,20 @@ int msdf_pixel_batch(const int64_t* ray_ids, int64_t n, const float* poses, cons
                      float* ray_dirs, float* ray_dirs_tmp, float* ray_cam_loc, float* ray_pose, int64_t* frame_idx,
                      float* gt_rgb, float* gt_depth, float* gt_mask, float* gt_normal, int* bad_flag, void* stream);
 
+/* Coarse-to-fine SDF volume of one marching-cubes crop ("next" row f4; utils/plots.py:131-194, get_surface_sliding).
+ * Level s (0 = finest) of a crop with crop_n samples per axis over [lo, hi] (HOST double[3]) has n = crop_n >> s cells
+ * per axis, cell coordinates = mean of the 2^s fine linspace samples they cover.
+ * msdf_sdfgrid_level_points: for every cell of the level whose parent cell is masked (parent_mask [(n/2)^3] bytes, NULL =
+ *   all cells) append its point to points [<= n^3, 3] (order unspecified), store the list position in slot [n^3] (-1 =
+ *   not evaluated) and count them in *counter (device int the caller zeroes).
+ * msdf_sdfgrid_level_assemble: level[c] = values[slot[c]] if evaluated else parent[parent cell of c] (nearest upsample);
+ *   mask[c] = |level[c]| < threshold (mask may be NULL for the finest level; parent may be NULL when every cell was
+ *   evaluated). */
+int msdf_sdfgrid_level_points(const double* lo, const double* hi, int crop_n, int level_shift, const unsigned char* parent_mask,
+                              int* slot, float* points, int* counter, void* stream);
+int msdf_sdfgrid_level_assemble(int n, const int* slot, const float* values, const float* parent, float threshold,
+                                float* level, unsigned char* mask, void* stream);
+
 /* ------------------------------------------------------------------ compositing ---------------------------
  * LaplaceDensity (density.py:21-30) + volume_rendering (network.py:626-640) + the weighted sums and the
  * normal-map rotation (network.py:552-562,603-616), one warp per ray.

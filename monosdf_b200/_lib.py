@@ -64,6 +64,8 @@ _SIGNATURES = {
                                     POINTER(MlpGrads), POINTER(MlpGrads), _P, _P, _P, c_size_t, _P]),
     "msdf_ray_points": (c_int, [_P, _P, _P, c_int64, c_int, _P, _P]),
     "msdf_camera_rays": (c_int, [_P, _P, _P, c_int64, c_int64, _P, _P, _P]),
+    "msdf_sdfgrid_level_points": (c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "msdf_sdfgrid_level_assemble": (c_int, [c_int, _P, _P, _P, c_float, _P, _P, _P]),
     "msdf_pixel_batch": (c_int, [_P, c_int64, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "msdf_render_forward": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "msdf_render_backward": (c_int, [_P, _P, _P, _P, c_int64, c_int, _P, _P, c_int64, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -630,6 +630,51 @@ def model_forward(params: Dict[str, Tensor], cfg: ModelCfg, inp: Dict[str, Tenso
 
 
 # --------------------------------------------------------------------------------------
+# utils/plots.py:131-194  (get_surface_sliding: the SDF volume of one crop, coarse to fine with masks)
+# --------------------------------------------------------------------------------------
+def sdf_volume_pyramid(sdf: Callable[[Tensor], Tensor], lo, hi, crop_n: int, trace: Optional[list] = None) -> Tensor:
+    """The volume `z` of plots.py:194 for the crop [lo, hi]^3 with crop_n samples per axis; sdf: [M,3] -> [M]."""
+    avg_pool_3d = torch.nn.AvgPool3d(2, stride=2)                      # :105
+    upsample = torch.nn.Upsample(scale_factor=2, mode="nearest")       # :106
+    x = np.linspace(lo[0], hi[0], crop_n)                              # :135-137
+    y = np.linspace(lo[1], hi[1], crop_n)
+    z = np.linspace(lo[2], hi[2], crop_n)
+    xx, yy, zz = torch.meshgrid(torch.tensor(x), torch.tensor(y), torch.tensor(z), indexing="ij")   # :142
+    points = torch.vstack([xx.flatten(), yy.flatten(), zz.flatten()]).T.float()                     # :143
+    points = points.reshape(crop_n, crop_n, crop_n, 3).permute(3, 0, 1, 2)                          # :154
+    pyramid = [points]
+    for _ in range(3):                                                 # :156-158
+        points = avg_pool_3d(points[None])[0]
+        pyramid.append(points)
+    pyramid = pyramid[::-1]
+    mask = None
+    threshold = 2 * (hi[0] - lo[0]) / crop_n * 8                       # :162
+    pts_sdf = None
+    for pid, pts in enumerate(pyramid):                                # :164-190
+        coarse_n = pts.shape[-1]
+        pts = pts.reshape(3, -1).permute(1, 0).contiguous()
+        if mask is None:
+            pts_sdf = sdf(pts).reshape(-1)
+            if trace is not None:
+                trace.append((coarse_n, pts.shape[0]))
+        else:
+            mask = mask.reshape(-1)
+            pts_to_eval = pts[mask]
+            if pts_to_eval.shape[0] > 0:
+                pts_sdf[mask] = sdf(pts_to_eval.contiguous()).reshape(-1)
+            if trace is not None:
+                trace.append((coarse_n, pts_to_eval.shape[0]))
+        if pid < 3:
+            mask = torch.abs(pts_sdf) < threshold
+            mask = mask.reshape(coarse_n, coarse_n, coarse_n)[None, None]
+            mask = upsample(mask.float()).bool()
+            pts_sdf = pts_sdf.reshape(coarse_n, coarse_n, coarse_n)[None, None]
+            pts_sdf = upsample(pts_sdf).reshape(-1)
+        threshold /= 2.0
+    return pts_sdf.reshape(crop_n, crop_n, crop_n)
+
+
+# --------------------------------------------------------------------------------------
 # pixel-mode data path: SceneDatasetDN.convert_to_pixels + __getitem__ + collate_fn
 # (datasets/scene_dataset.py:258-260, 269-307, 374-401, 438-464)
 # --------------------------------------------------------------------------------------

@@ -1,0 +1,65 @@
+"""Coarse-to-fine SDF volume for marching cubes: oracle/port.sdf_volume_pyramid restates
+utils/plots.py:131-194; monosdf_b200.mesh.sdf_volume_pyramid (csrc/sdfgrid.cu + the SDF-only field kernels) must give
+the same volume: same cells evaluated at every level (index work), values within fp32 tolerance."""
+import pytest
+import torch
+
+from oracle import port
+from tests.helpers import build_model, params_of
+
+
+def _sphere(r=0.6):
+    return lambda p: p.norm(dim=-1) - r
+
+
+def test_oracle_pyramid_equals_dense_evaluation_near_the_surface():
+    """Masked evaluation is exact wherever the finest mask is set, and only a fraction of the cells is evaluated."""
+    n = 32
+    trace = []
+    vol = port.sdf_volume_pyramid(_sphere(), (-1.0,) * 3, (1.0,) * 3, n, trace)
+    g = torch.linspace(-1.0, 1.0, n, dtype=torch.float64)
+    dense = _sphere()(torch.stack(torch.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).float()).reshape(n, n, n)
+    band = dense.abs() < 2 * 2.0 / n                    # well inside the finest threshold 2 * (2 / n) * 8 / 8
+    assert bool(band.any())
+    assert torch.allclose(vol[band], dense[band], atol=1e-6)
+    assert [t[0] for t in trace] == [4, 8, 16, 32]
+    assert trace[0][1] == 64 and trace[3][1] < n ** 3                  # coarsest level dense, finest level masked
+    assert torch.equal(vol < 0, dense < 0)                              # the sign (inside / outside) is right everywhere
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,n", [("mlp_small", 32), ("mlp_full", 64)])
+def test_device_pyramid_matches_oracle(golden, case, n):
+    from monosdf_b200.mesh import sdf_volume_pyramid
+    fx = golden(case)
+    model = build_model(fx, "cuda").eval()
+    cfg = port.cfg_from_conf(fx["conf"])
+    params = params_of(model)
+    lo, hi = (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0)
+    trace = []
+    with torch.no_grad():
+        vol_o = port.sdf_volume_pyramid(lambda p: port.sdf_vals(params, cfg, p).reshape(-1), lo, hi, n, trace)
+    stats = []
+    vol = sdf_volume_pyramid(model.implicit_network.get_sdf_vals, lo, hi, n, stats=stats).cpu()
+    assert vol.shape == vol_o.shape
+    # same number of cells evaluated at every level (a cell whose |sdf| sits within rounding of the threshold may flip)
+    for (n_o, c_o), (n_d, c_d) in zip(trace, stats):
+        assert n_o == n_d and abs(c_o - c_d) <= max(8, c_o // 500), (trace, stats)
+    close = (vol - vol_o).abs() <= 1e-4 * (1.0 + vol_o.abs())
+    assert float(close.float().mean()) > 0.999
+    band = vol_o.abs() < 2.0 / n                       # the cells marching cubes interpolates between
+    assert bool(band.any()) and bool(close[band].all())
+    assert float(((vol < 0) == (vol_o < 0)).float().mean()) > 0.9999
+
+
+@pytest.mark.gpu
+def test_surface_volumes_crops():
+    """get_surface_sliding's crop loop (plots.py:110-128) at a reduced size: origin, spacing, one volume per crop."""
+    from monosdf_b200 import mesh
+    sdf = lambda p: p.norm(dim=-1) - 0.7       # noqa: E731
+    out = list(mesh.surface_volumes(sdf, resolution=128, grid_boundary=(-1.0, 1.0)))
+    assert len(out) == 1
+    origin, spacing, vol = out[0]
+    assert vol.shape == (128, 128, 128) and vol.dtype.name == "float32"
+    assert abs(spacing[0] - 2.0 / 127) < 1e-12 and float(origin[0]) == -1.0
+    assert vol[64, 64, 64] < 0 < vol[0, 0, 0]
