@@ -592,23 +592,27 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 // ==========================================================================================================
 // dW += X^T Y  (both operands MN-major), split over the rows
 // ==========================================================================================================
-// grid (i_tiles, j_tiles, splits).  X tile: BI = 128 columns of X = 2 boxes of [64 rows(k) x 64 cols]; Y tile: BJ
-// columns (multiple of 64, <= 256) = BJ/64 boxes.  One k-block = 64 rows.
+// grid (i_tiles, j_tiles, splits).  X tile: BI = 64 nbx columns of X (nbx = 2 or 4 boxes of [64 rows(k) x 64 cols]:
+// one or two 128-row accumulators); Y tile: BJ columns (multiple of 64, <= 256) = BJ/64 boxes.  One k-block = 64 rows.
+// The kernel is bound by shared-memory bandwidth (per stage: TMA writes + MMA operand reads + the format conversion
+// below), so the 256-column X tile matters: the Y boxes are written / converted once for two accumulators' worth of
+// MMAs (per 128x256 unit of work 112 KB instead of 160 KB of shared-memory traffic in the mixed-format products).
 template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
-k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int BJ,
+k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int nbx_, int BJ,
            int64_t rows_per_split, int stages, int x_fmt, int y_fmt, Epi epi, float* __restrict__ colsum, int colsum_n,
            int colsum_perm, int colsum_shift) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     constexpr uint32_t kBox = 64 * 128;                          // 64 k-rows x 128 B
-    const uint32_t nbx = 2, nby = (uint32_t)BJ / 64u;
+    const uint32_t nbx = (uint32_t)nbx_, nby = (uint32_t)BJ / 64u;
+    const uint32_t tmem_cols = nbx > 2 ? 512u : 256u;
     const uint32_t stage_bytes = (nbx + nby) * kBox;
     const uint32_t sE = base + (uint32_t)stages * stage_bytes;
     Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)stages * stage_bytes + kEpiWarps * kSlotBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = blockIdx.x * 128, j0 = blockIdx.y * BJ;
+    const int i0 = blockIdx.x * (int)(nbx * 64u), j0 = blockIdx.y * BJ;
     const int64_t r0 = (int64_t)blockIdx.z * rows_per_split;
     const int64_t r1 = (r0 + rows_per_split < Mrows) ? r0 + rows_per_split : Mrows;
     const bool do_colsum = colsum != nullptr && blockIdx.y == 0;   // out[i] += sum_m X[m, i]: bias gradients for free
@@ -635,7 +639,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         mbar_init(smem_u32(&bars->tfull[0]), 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), 256);
+    if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -666,9 +670,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
 #pragma unroll
                 for (int k = 0; k < 64 / UMMA_K; ++k) {
                     // MN-major SW128: 64-element groups along M/N are kBox apart (LBO), 8-row k groups 1024 B apart (SBO)
-                    const uint64_t da = smem_desc(st + k * (UMMA_K * 128), kBox, 1024);
                     const uint64_t db = smem_desc(st + nbx * kBox + k * (UMMA_K * 128), kBox, 1024);
-                    umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (uint32_t h = 0; h < nbx / 2; ++h) {          // one 128-row accumulator per pair of X boxes
+                        const uint64_t da = smem_desc(st + h * 2 * kBox + k * (UMMA_K * 128), kBox, 1024);
+                        umma_bf16(tmem_base + h * 256u, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                 }
                 umma_commit(smem_u32(&bars->empty[s]));
                 if (++s == stages) { s = 0; ph ^= 1u; }
@@ -682,10 +688,11 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             // place (element-wise, so the swizzle does not matter; 16-byte vectors, thread t takes vectors t, t + 256,
             // ...), make the writes visible to the tensor core (async proxy) and release the stage to the MMA warp;
             // (2) read the X boxes out of shared memory (the operand is there anyway) and accumulate its column sums.
-            // Thread t: column pair (t & 63) of the 128-column tile, k-rows 16 (t >> 6) .. +15 of the 64-row block; a
-            // warp reads whole 128-byte swizzle rows.
+            // Thread t: column pair t % (32 nbx) of the X tile, k-rows rpg (t / (32 nbx)) .. + rpg - 1 of the 64-row block
+            // (rpg = 16 for the 128-column tile, 32 for the 256-column tile); a warp reads whole 128-byte swizzle rows.
             const int t = (int)threadIdx.x - 64;
-            const int pi = t & 63, g = t >> 6;
+            const int pairs = (int)nbx * 32, rpg = 64 / (kEpiWarps * 32 / pairs);
+            const int pi = t % pairs, g = t / pairs;
             const int c = (pi & 31) * 2;
             const uint32_t box_off = (uint32_t)(pi >> 5) * kBox;
             const uint32_t conv_off = x_fmt == kF16 ? 0u : nbx * kBox;
@@ -713,9 +720,9 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 }
                 if (do_colsum) {
                     const uint32_t st = base + s * stage_bytes + box_off;
-#pragma unroll
-                    for (int kk = 0; kk < 16; ++kk) {
-                        const int k = g * 16 + kk;
+#pragma unroll 16
+                    for (int kk = 0; kk < rpg; ++kk) {
+                        const int k = g * rpg + kk;
                         uint32_t w;
                         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(st + (uint32_t)(k * 128 + ((((c >> 3) ^ (k & 7)) << 4) | ((c & 7) * 2)))) : "memory");
                         s0 += x_bf16 ? WarpIO::lo_of<kBF16>(w) : WarpIO::lo_of<kF16>(w);
@@ -739,15 +746,18 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         tc_fence_after();
         WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)i0 + q * 32, (int64_t)1 << 40, 0u};
         io.init();
-        for (int c = half; c < chunks; c += 2) {
-            float v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c * 32u, v);
-            epi.chunk(io, j0 + c * 32, v, nullptr);
+        for (uint32_t h = 0; h < nbx / 2; ++h) {
+            io.retile((int64_t)i0 + h * 128 + q * 32);
+            for (int c = half; c < chunks; c += 2) {
+                float v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256u + (uint32_t)c * 32u, v);
+                epi.chunk(io, j0 + c * 32, v, nullptr);
+            }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, tmem_cols); }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -844,13 +854,14 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     int rc = make_map(&mX, X, x_fmt, M, Ci, ldx, 64, what); if (rc) return rc;
     rc = make_map(&mY, Y, y_fmt, M, Cj, ldy, 64, what); if (rc) return rc;
     const int BJ = Cj < 256 ? Cj : 256;
-    const int it = (Ci + 127) / 128, jt = (Cj + BJ - 1) / BJ;
+    const int nbx = Ci > 128 ? 4 : 2;                       // X tile of 256 (two accumulators) or 128 columns
+    const int it = (Ci + nbx * 64 - 1) / (nbx * 64), jt = (Cj + BJ - 1) / BJ;
     int splits = (sm_count() + it * jt - 1) / (it * jt);
     int64_t rps = (M + splits - 1) / splits;
     rps = (rps + 63) / 64 * 64;
     if (rps < 256) rps = 256;
     splits = (int)((M + rps - 1) / rps);
-    const uint32_t stage_bytes = (2 + BJ / 64) * 64 * 128;
+    const uint32_t stage_bytes = (nbx + BJ / 64) * 64 * 128;
     const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes;
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (stages > 6) stages = 6;
@@ -863,7 +874,7 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st, (double)M * 2.0 * (double)(Ci + Cj));
-    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift);
+    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, nbx, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
