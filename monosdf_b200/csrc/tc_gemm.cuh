@@ -30,7 +30,9 @@ constexpr int BM = 128;            // rows per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = (2 + kEpiWarps) * 32;
+constexpr int kThreads = (2 + kEpiWarps) * 32;        // k_tc_wgrad: producer warp, MMA warp, 8 epilogue warps
+constexpr int kGemmThreads = (4 + kEpiWarps) * 32;    // k_tc_gemm: warpgroup 0 = {producer, MMA, 2 idle warps}, then 8 epilogue warps
+constexpr int kRegsLight = 40, kRegsEpi = 232;        // setmaxnreg split of k_tc_gemm: 128 x 40 + 256 x 232 = 384 x 168
 constexpr int kMaxStages = 8;
 constexpr uint32_t kStageBytesA = BM * BK * 2;   // 16 KB
 constexpr uint32_t kTmemCols = 512;
@@ -434,10 +436,12 @@ constexpr int kMaxChunksPerWarp = 4;   // 256 accumulator columns / 32 / 2 warps
 // ==========================================================================================================
 // C = epi(A W^T), weights resident
 // ==========================================================================================================
-// 320 threads = 10 warps are allocated as 12 (granularity 4), so the register cap is 65536 / 384 = 168 per thread: the
-// epilogues keep their second read-back operand packed (unstage_packed) to stay below it without spilling
+// 384 threads = 3 warpgroups, launched with 168 registers per thread (65536 / 384).  Warpgroup 0 (TMA producer, MMA
+// issuer: single-thread roles) shrinks to 40 registers with setmaxnreg and the two epilogue warpgroups grow to 232: room
+// for a deeper rolling prefetch of the operands the epilogue reads back (ncu: 27 % of the EpiRev samples sat on the
+// long-scoreboard stall of the staging store that consumes a prefetched vector -- not enough bytes in flight).
 template <class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, int64_t M, int BN, int KB,
           int stages, int a_fmt, int w_fmt, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
@@ -461,9 +465,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
-    if (threadIdx.x >= 64) {                                    // epilogue warps stage the column vector
+    if (threadIdx.x >= 128) {                                   // epilogue warps stage the column vector
         const float* cv = epi.colvec();
-        const int j = (int)threadIdx.x - 64;
+        const int j = (int)threadIdx.x - 128;
         if (j < 256) {
             const float x = (cv != nullptr && j < epi.N) ? __ldg(cv + j) : 0.f;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(sV + (uint32_t)j * 4u), "f"(x) : "memory");
@@ -474,6 +478,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
+    // (each setmaxnreg sits INSIDE its role's branch: after a merge point ptxas budgets for the smaller of the two counts)
+    if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLight));
     if (warp == 0) {
         if (lane == 0) {
             // ---- TMA producer: the layer's weights once, then the ring of A tiles
@@ -517,13 +524,16 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
             }
         }
         __syncwarp();
+    }
     } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
         // ---- epilogue: TMEM lane quadrant = warp % 4; the two warps of a quadrant interleave 32-column chunks
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int q = warp & 3, half = (warp - 4) >> 2;
         const int chunks = (BN + 31) / 32;
         uint32_t it = 0;
-        uint4 pre[2][pre_regs<Epi>()];
-        WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)blockIdx.x * BM + q * 32, M, sV};
+        constexpr int kDepth = Epi::kPre >= 1 ? 4 : 2;      // chunks in flight per warp (4 = a whole tile's worth)
+        uint4 pre[kDepth][pre_regs<Epi>()];
+        WarpIO io{sE + (uint32_t)(warp - 4) * kSlotBytes, lane, (int64_t)blockIdx.x * BM + q * 32, M, sV};
         io.init();
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
@@ -551,7 +561,6 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 // Rolling prefetch of the epilogue's bf16 operands, kDepth chunks ahead (across tile boundaries): the
                 // registers of a consumed chunk are refilled at once with the loads of chunk + kDepth, so global latency
                 // is covered by the math / stores of the chunks in between and never by an idle warp.
-                constexpr int kDepth = 2;
                 if (it == 0) {
 #pragma unroll
                     for (int i = 0; i < kDepth; ++i)
@@ -570,11 +579,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             tmem_ld32(tacc + (uint32_t)c * 32u, v);
                             epi.chunk(io, c * 32, v, pre[k]);
                         }
-                        if (ii == 0) {                                          // refill: chunk + kDepth of this tile ...
+                        if (ii + 1 < kMaxChunksPerWarp / kDepth) {             // refill: chunk + kDepth of this tile ...
                             if (c + 2 * kDepth < chunks) epi.prefetch(io, (c + 2 * kDepth) * 32, pre[k]);
-                        } else if (has_next && c - 2 * kDepth < chunks) {       // ... or the matching chunk of the next tile
+                        } else if (has_next && half + 2 * k < chunks) {         // ... or chunk k of the next tile
                             io.pf_row_shift = (int64_t)gridDim.x * BM;
-                            epi.prefetch(io, (c - 2 * kDepth) * 32, pre[k]);
+                            epi.prefetch(io, (half + 2 * k) * 32, pre[k]);
                             io.pf_row_shift = 0;
                         }
                     }
@@ -832,7 +841,7 @@ int launch_gemm(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, const 
     // algorithmic bytes: the A tile once, plus every bf16 operand the epilogue reads back and writes (epi.N real columns)
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
                                      (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(Epi::kPre + Epi::kStores)));
-    k_tc_gemm<Epi><<<grid, kThreads, smem, st>>>(mA, mW, M, BN, KB, stages, a_fmt, w_fmt, epi);
+    k_tc_gemm<Epi><<<grid, kGemmThreads, smem, st>>>(mA, mW, M, BN, KB, stages, a_fmt, w_fmt, epi);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
