@@ -82,7 +82,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: samples taken before it (warm-up) are not reported."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -90,7 +94,9 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for t, r in self.rows:
+            if t < getattr(self, "t0", 0.0):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx = float(r[1])
@@ -230,12 +236,15 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    for _ in range(max(args.warmup, 3)):
-        step(res, res_gt)
-    rounds = model.ray_sampler.last_total_iters
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, first query) stalls kernel launches for
+    # a few hundred ms, which used to land in the first timed steps; only samples taken after mark() are reported
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(max(args.warmup, 3)):
+        step(res, res_gt)
+    rounds = model.ray_sampler.last_total_iters
+    clocks.mark()
     l0 = _lib.launch_count()
     ms = timed(lambda: step(res, res_gt), args.steps)
     launches = _lib.launch_count() - l0
