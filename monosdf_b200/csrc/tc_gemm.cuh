@@ -531,7 +531,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int q = warp & 3, half = (warp - 4) >> 2;
         const int chunks = (BN + 31) / 32;
         uint32_t it = 0;
-        constexpr int kDepth = Epi::kPre >= 1 ? 4 : 2;      // chunks in flight per warp (4 = a whole tile's worth)
+        constexpr int kDepth = Epi::kPre == 1 ? 4 : 2;      // chunks in flight per warp (4 = a whole tile's worth)
         uint4 pre[kDepth][pre_regs<Epi>()];
         WarpIO io{sE + (uint32_t)(warp - 4) * kSlotBytes, lane, (int64_t)blockIdx.x * BM + q * 32, M, sV};
         io.init();
@@ -569,14 +569,20 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const bool has_next = tile + gridDim.x < num_tiles;
                 mbar_wait(smem_u32(&bars->tfull[a]), aph);
                 tc_fence_after();
+                // accumulator chunks double buffered in registers like above (the 232-register budget pays for it)
+                uint32_t r[2][32];
+                if (half < chunks) tmem_ld32_issue(tacc + (uint32_t)half * 32u, r[0]);
 #pragma unroll 1
-                for (int ii = 0; ii < kMaxChunksPerWarp / kDepth; ++ii) {      // compact code: two 2-chunk bodies
+                for (int ii = 0; ii < kMaxChunksPerWarp / kDepth; ++ii) {
 #pragma unroll
                     for (int k = 0; k < kDepth; ++k) {
                         const int c = half + 2 * (ii * kDepth + k);
                         if (c < chunks) {
+                            tmem_ld32_wait(r[k & 1]);
+                            if (c + 2 < chunks) tmem_ld32_issue(tacc + (uint32_t)(c + 2) * 32u, r[(k + 1) & 1]);
                             float v[32];
-                            tmem_ld32(tacc + (uint32_t)c * 32u, v);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[k & 1][j]);
                             epi.chunk(io, c * 32, v, pre[k]);
                         }
                         if (ii + 1 < kMaxChunksPerWarp / kDepth) {             // refill: chunk + kDepth of this tile ...
