@@ -1,9 +1,10 @@
 """GPU parity of the hash-grid encoder (operator boundary and inside the field) against the CPU restatement
 oracle/port.py:hash_encode (hashencoder.cu:35-93,104-254 restated in differentiable torch ops).
 
-The reference's own hash kernels are CUDA-only and cannot run in the build container, so for this component the
-oracle is pinned by construction (indexing, smoothstep and dy_dx formulas cited line by line), not by golden
-vectors: DESIGN.md lists it as "parity unpinned".
+The reference's own hash kernels are CUDA-only and cannot run in the build container; they are compiled there
+(oracle/build_ref_hashencoder.py) and run on the GPU box by tests/test_gpu_hashgrid_reference.py, which pins
+msdf_hash_encode_* to them by execution.  This file pins the restatement (used by the oracle's model_forward for Grid
+nets) to the same CUDA path, and covers what the reference kernels cannot (C = 1, the fused row variants).
 """
 import copy
 
