@@ -544,6 +544,54 @@ k_rowdot(const T* __restrict__ A, int64_t lda, const float* __restrict__ W, int6
     }
 }
 
+// sdf head of the tensor-core mode: out[m] = sum_k A[m,k] W[k] + b, A 16-bit with K % 8 == 0 and 16-byte aligned rows.
+// One warp per row like k_rowdot, but every lane reads 16-byte vectors (a 256-wide row is ONE request per warp instead
+// of eight 64-byte ones) and keeps its slice of W in registers across the rows the warp walks over.
+template <class TA>
+__global__ void __launch_bounds__(256)
+k_rowdot1_vec(const TA* __restrict__ A, int64_t lda, const float* __restrict__ W, const float* __restrict__ b, int64_t M, int K,
+              float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    constexpr int kMaxVec = 2;                           // K <= 512
+    float w[kMaxVec][8];
+#pragma unroll
+    for (int v = 0; v < kMaxVec; ++v)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const int k = (v * 32 + lane) * 8 + j; w[v][j] = k < K ? __ldg(W + k) : 0.f; }
+    const float bias = b[0];
+    constexpr int R = 4;                                 // rows in flight per warp: all loads issued before the math
+    for (int64_t m0 = warp * R; m0 < M; m0 += nwarps * R) {
+        uint4 q[R][kMaxVec];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int v = 0; v < kMaxVec; ++v) {
+                const int k0 = (v * 32 + lane) * 8;
+                q[r][v] = make_uint4(0u, 0u, 0u, 0u);
+                if (m0 + r < M && k0 < K) q[r][v] = *reinterpret_cast<const uint4*>(A + (m0 + r) * lda + k0);
+            }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float s = 0.f;
+#pragma unroll
+            for (int v = 0; v < kMaxVec; ++v) {
+                constexpr int F = Fmt16<TA>::value;
+                const uint32_t ww[4] = {q[r][v].x, q[r][v].y, q[r][v].z, q[r][v].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    s = fmaf(msdf_tc::WarpIO::lo_of<F>(ww[j]), w[v][2 * j], s);
+                    s = fmaf(msdf_tc::WarpIO::hi_of<F>(ww[j]), w[v][2 * j + 1], s);
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (lane == 0 && m0 + r < M) out[m0 + r] = s + bias;
+        }
+    }
+}
+
 __device__ __forceinline__ float act_grad(int act, float y) {   // d act / d pre as a function of the output y
     return act == kActSigmoid ? y * (1.0f - y) : (act == kActRelu ? (y > 0.f ? 1.f : 0.f) : 1.f);
 }
@@ -1391,7 +1439,15 @@ int forward_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc, Fw<T>* feat, int64
         RUN((gemm_nt<T>(c, n, l, b.H[l], ldin, Mc, 0, n.out[l], e, "sdf forward layer")));
     }
     const int l = n.L - 1;
-    k_rowdot<1, Fw<T>><<<nblk(Mc, 8), 256, 0, c.st>>>(b.H[l], b.ldh, n.W[l], n.ldw[l], n.b[l], Mc, 1, n.in[l], kActNone, b.sdf_raw, 1);
+    bool vec = false;
+    if constexpr (kIsBf16<T>) vec = n.in[l] % 8 == 0 && n.in[l] <= 512;
+    if constexpr (kIsBf16<T>) if (vec) {
+        const int64_t blocks = msdf_div_up(Mc, 8 * 16);      // 8 warps per block, 16 rows (4 groups of 4) per warp
+        k_rowdot1_vec<Fw<T>><<<(unsigned)(blocks > 0 ? blocks : 1), 256, 0, c.st>>>(b.H[l], b.ldh, n.W[l], n.b[l], Mc, n.in[l], b.sdf_raw);
+    }
+    if (!vec) {
+        k_rowdot<1, Fw<T>><<<nblk(Mc, 8), 256, 0, c.st>>>(b.H[l], b.ldh, n.W[l], n.ldw[l], n.b[l], Mc, 1, n.in[l], kActNone, b.sdf_raw, 1);
+    }
     LAUNCHED("sdf head");
     if (feat != nullptr && n.out[l] > 1) {
         EpiBias<T> e{};
