@@ -192,6 +192,14 @@ struct WarpIO {
     int rows_left;      // M - row0, clamped to [0, 32]
     mutable uint32_t flip;   // bf16 stagings alternate between the two 2 KB halves of the slot: one __syncwarp each
     int64_t pf_row_shift;    // prefetch() addresses rows row0 + pf_row_shift (set while prefetching for the next tile)
+    // Second prefetch path.  ptxas puts EVERY register prefetch (ld.global -> uint4) of the epilogue on one scoreboard
+    // (tools/sass_scoreboards.py), so the staging store of a chunk waits for ALL outstanding loads, the refills issued
+    // one chunk ago included: a register ring is one chunk deep whatever its size.  Odd ring slots therefore go through
+    // cp.async into a per-warp landing buffer (abuf: 2 KB per operand, the layout unstage() writes), tracked by
+    // cp.async.wait_all instead of that scoreboard: each mechanism then only ever waits for loads issued two chunks ago.
+    uint32_t abuf;           // shared-memory address of the landing buffer, 0 = not available (wide-K launches)
+    mutable int amode;       // 1 while the engine prefetches / consumes an odd slot
+    mutable const uint4* qbase;   // register array of the slot in flight: (q - qbase) / 4 = operand index
 
     __device__ __forceinline__ void init() {
         const int x = (lane >> 1) & 3, r = lane >> 2, pc = lane & 3;
@@ -200,6 +208,8 @@ struct WarpIO {
         trn = (uint32_t)(r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
         flip = 0u;
         pf_row_shift = 0;
+        amode = 0;
+        qbase = nullptr;
         retile(row0);
     }
     __device__ __forceinline__ void retile(int64_t new_row0) {
@@ -223,6 +233,11 @@ struct WarpIO {
     // hidden: prefetch() issues the loads (lane t fetches 16-byte piece t&3 of rows i*8 + t/4; predicated, rows >= M
     // are left undefined and must not be stored), unstage() transposes them through the slot so that
     // out[j] = P[row(), n0 + j].  Requires 16-byte aligned P + n0 and ld % 8 == 0.
+    __device__ __forceinline__ uint32_t abuf_of(const uint4* q) const { return abuf + (uint32_t)(q - qbase) * 512u; }   // 4 uint4 = 2 KB
+    __device__ __forceinline__ void async_ready() const {
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+    }
     __device__ __forceinline__ void prefetch(const void* Pv, int64_t ld, int n0, uint4 q[4]) const {
         const uint16_t* P = reinterpret_cast<const uint16_t*>(Pv);     // any 16-bit element type
         const int64_t base_row = row0 + pf_row_shift;        // pf_row_shift != 0: the same rows of a later tile
@@ -231,6 +246,18 @@ struct WarpIO {
         const char* base = reinterpret_cast<const char*>(P + (base_row + (lane >> 2)) * ld + n0 + (lane & 3) * 8);
         const int64_t step = ld * 16;            // 8 rows, in bytes
         const int r = lane >> 2;
+        if (amode) {
+            // rows >= M: zero fill (source size 0; the address is kept inside the matrix)
+            const uint32_t dst = abuf_of(q) + trn;
+            __syncwarp();                         // every lane is done reading the buffer's previous contents
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool on = (i * 8 + r) < left;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)i * 512u), "l"(on ? base + i * step : reinterpret_cast<const char*>(P)),
+                             "r"(on ? 16u : 0u) : "memory");
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const uint32_t on = (i * 8 + r) < left ? 1u : 0u;
@@ -249,12 +276,18 @@ struct WarpIO {
     }
     template <int F>
     __device__ __forceinline__ void unstage(const uint4 q[4], float out[32]) const {
-        const uint32_t h = slot + flip;
-        flip ^= 2048u;
+        uint32_t h;
+        if (amode) {
+            async_ready();
+            h = abuf_of(q);
+        } else {
+            h = slot + flip;
+            flip ^= 2048u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
-        __syncwarp();
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
+            __syncwarp();
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             uint32_t w[4];
@@ -268,12 +301,18 @@ struct WarpIO {
     }
     // same, but the row stays packed: w[p * 4 + j] holds columns p*8 + 2j (low half) and p*8 + 2j + 1 (high half)
     __device__ __forceinline__ void unstage_packed(const uint4 q[4], uint32_t w[16]) const {
-        const uint32_t h = slot + flip;
-        flip ^= 2048u;
+        uint32_t h;
+        if (amode) {
+            async_ready();
+            h = abuf_of(q);
+        } else {
+            h = slot + flip;
+            flip ^= 2048u;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
-        __syncwarp();
+            for (int i = 0; i < 4; ++i)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
+            __syncwarp();
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p)
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[4 * p]), "=r"(w[4 * p + 1]), "=r"(w[4 * p + 2]), "=r"(w[4 * p + 3]) : "r"(h + own[p]) : "memory");
@@ -443,7 +482,7 @@ constexpr int kMaxChunksPerWarp = 4;   // 256 accumulator columns / 32 / 2 warps
 template <class Epi>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, int64_t M, int BN, int KB,
-          int stages, int a_fmt, int w_fmt, Epi epi) {
+          int stages, int abytes, int a_fmt, int w_fmt, Epi epi) {    // abytes: cp.async landing buffer per epilogue warp (0: none)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -452,7 +491,9 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
     const uint32_t sA = sW + (uint32_t)KB * w_block;            // stages x 16 KB
     const uint32_t sE = sA + (uint32_t)stages * kStageBytesA;   // kEpiWarps staging slots
     const uint32_t sV = sE + kEpiWarps * kSlotBytes;            // per-column vector (bias), 256 floats
-    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)KB * w_block + (size_t)stages * kStageBytesA + kEpiWarps * kSlotBytes + kColVecBytes);
+    const uint32_t sX = sV + kColVecBytes;                      // cp.async landing buffers, kEpiWarps x abytes
+    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)KB * w_block + (size_t)stages * kStageBytesA + kEpiWarps * kSlotBytes + kColVecBytes +
+                                                 (size_t)kEpiWarps * abytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = (M + BM - 1) / BM;
 
@@ -531,10 +572,12 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         const int q = warp & 3, half = (warp - 4) >> 2;
         const int chunks = (BN + 31) / 32;
         uint32_t it = 0;
-        constexpr int kDepth = Epi::kPre == 1 ? 4 : 2;      // chunks in flight per warp (4 = a whole tile's worth)
+        constexpr int kDepth = 2;                           // ring slots per warp: slot 0 in registers, slot 1 via cp.async
         uint4 pre[kDepth][pre_regs<Epi>()];
         WarpIO io{sE + (uint32_t)(warp - 4) * kSlotBytes, lane, (int64_t)blockIdx.x * BM + q * 32, M, sV};
         io.init();
+        io.abuf = abytes > 0 ? sX + (uint32_t)(warp - 4) * (uint32_t)abytes : 0u;
+        const bool use_async = abytes > 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
             const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
             io.retile(tile * BM + q * 32);
@@ -564,7 +607,11 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 if (it == 0) {
 #pragma unroll
                     for (int i = 0; i < kDepth; ++i)
-                        if (half + 2 * i < chunks) epi.prefetch(io, (half + 2 * i) * 32, pre[i]);
+                        if (half + 2 * i < chunks) {
+                            io.amode = (i & 1) && use_async; io.qbase = pre[i];
+                            epi.prefetch(io, (half + 2 * i) * 32, pre[i]);
+                            io.amode = 0;
+                        }
                 }
                 const bool has_next = tile + gridDim.x < num_tiles;
                 mbar_wait(smem_u32(&bars->tfull[a]), aph);
@@ -583,8 +630,10 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             float v[32];
 #pragma unroll
                             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[k & 1][j]);
+                            io.amode = (k & 1) && use_async; io.qbase = pre[k];
                             epi.chunk(io, c * 32, v, pre[k]);
                         }
+                        io.amode = (k & 1) && use_async; io.qbase = pre[k];
                         if (ii + 1 < kMaxChunksPerWarp / kDepth) {             // refill: chunk + kDepth of this tile ...
                             if (c + 2 * kDepth < chunks) epi.prefetch(io, (c + 2 * kDepth) * 32, pre[k]);
                         } else if (has_next && half + 2 * k < chunks) {         // ... or chunk k of the next tile
@@ -592,6 +641,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                             epi.prefetch(io, (half + 2 * k) * 32, pre[k]);
                             io.pf_row_shift = 0;
                         }
+                        io.amode = 0;
                     }
                 }
             }
@@ -831,7 +881,12 @@ int launch_gemm(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, const 
     rc = make_map(&mW, W, w_fmt, BN, Kp, ldw, BN, what); if (rc) return rc;
     const int KB = Kp / 64;
     const size_t wbytes = (size_t)KB * BN * 128;
-    const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes + kColVecBytes;
+    size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes + kColVecBytes;
+    // cp.async landing buffers of the epilogue's second prefetch path (2 KB per read-back operand and warp), when the
+    // weights leave room for them next to two A stages (the depth of the A ring does not matter: measured 2 = 3 = 4)
+    int abytes = Epi::kPre * 2048;
+    if (227 * 1024 < fixed + (size_t)kEpiWarps * abytes + wbytes + 2 * kStageBytesA) abytes = 0;
+    fixed += (size_t)kEpiWarps * abytes;
     int stages = (int)((227 * 1024 - fixed - wbytes) / kStageBytesA);
     if (stages > 6) stages = 6;
     if (stages < 2) { msdf_set_error("%s: weights do not leave room for the A ring", what); return MSDF_ERR_ARG; }
@@ -847,7 +902,7 @@ int launch_gemm(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, const 
     // algorithmic bytes: the A tile once, plus every bf16 operand the epilogue reads back and writes (epi.N real columns)
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
                                      (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(Epi::kPre + Epi::kStores)));
-    k_tc_gemm<Epi><<<grid, kGemmThreads, smem, st>>>(mA, mW, M, BN, KB, stages, a_fmt, w_fmt, epi);
+    k_tc_gemm<Epi><<<grid, kGemmThreads, smem, st>>>(mA, mW, M, BN, KB, stages, abytes, a_fmt, w_fmt, epi);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
