@@ -27,8 +27,7 @@ import torch  # noqa: E402
 METRIC = "training rays/s (fwd+bwd)"
 UNIT = "rays/s"
 # Algorithmic GFLOP per training ray, MLP conf, for k = 1..5 sampler rounds
-GFLOP_PER_RAY_MLP = {1: 0.800, 2: 0.918, 3: 1.035, 4: 1.153, 5: 1.270}
-GFLOP_PER_RAY_GRID = {1: 0.245, 2: 0.2665, 3: 0.288, 4: 0.3095, 5: 0.331}
+from monosdf_b200.roofline import GFLOP_PER_RAY_GRID, GFLOP_PER_RAY_MLP  # noqa: E402  (derived from the layer dims)
 CPU_SAMPLE_RAYS = 512
 
 
