@@ -1,5 +1,5 @@
 """Per-step times of the end-to-end training step with the allocator's cudaMalloc count and the SM clock beside them
-(is the step-to-step variation allocator churn or the power cap?):  python tools/step_jitter.py [rays] [steps]"""
+(is the step-to-step variation allocator churn or the power cap?):  python tools/step_jitter.py [rays] [steps] [mlp|grid]"""
 import os, subprocess, sys, warnings
 warnings.filterwarnings("ignore")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,7 +9,8 @@ from monosdf_b200.model.loss import MonoSDFLoss
 from monosdf_b200.model.network import MonoSDFNetwork
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-model = MonoSDFNetwork(confs.to_conf(confs.SCANNET_MLP)).to(dev).train()
+CONF = confs.KITCHEN_GRIDS if (len(sys.argv) > 3 and sys.argv[3] == "grid") else confs.SCANNET_MLP
+model = MonoSDFNetwork(confs.to_conf(CONF)).to(dev).train()
 with torch.no_grad():
     model.density.beta.fill_(0.01)
 model.set_precision("bf16")
