@@ -191,7 +191,8 @@ class _Field(Function):
             code = code.contiguous().float() if code is not None else None
         n_rays = view_dirs.shape[0] if use_color else 0
         saved = None
-        if any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
+        # (ctx.needs_input_grad reflects requires_grad even under torch.no_grad(): eval must not save activations)
+        if torch.is_grad_enabled() and any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
             nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), spec.flags)
             # free = what the driver reports plus what torch's caching allocator holds but has not handed out
             free = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
