@@ -195,8 +195,11 @@ class _Field(Function):
         if torch.is_grad_enabled() and any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
             nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), spec.flags)
             # free = what the driver reports plus what torch's caching allocator holds but has not handed out
-            free = torch.cuda.mem_get_info(dev)[0] + torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            free = torch.cuda.mem_get_info(dev)[0]
             pooled = sum(t.numel() for t in _lib.saved_pool.free if t.device == dev)
+            if not (0 < nbytes <= SAVED_ACTIVATION_FRACTION * (free + pooled)):
+                # second look (slow: builds the allocator's whole statistics dict, 0.15 ms per call)
+                free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
             if 0 < nbytes <= SAVED_ACTIVATION_FRACTION * (free + pooled):
                 saved = _lib.saved_pool.acquire(nbytes, dev)
         bwd_mode = _lib.MODE_BACKWARD if saved is not None else mode      # the saved layout needs the backward's workspace
