@@ -156,6 +156,18 @@ def _workspace_for(sdf_d, enc_d, col_d, cd_d, M, mode, flags, device):
     return _lib.workspace(min(need, WORKSPACE_CAP_BYTES), device)
 
 
+_CALLER_GRAD = [True]      # torch.is_grad_enabled() of the code that called _apply_field() (see _Field.forward)
+
+
+def _apply_field(*args):
+    """_Field.apply with the caller's grad mode on record."""
+    _CALLER_GRAD[0] = torch.is_grad_enabled()
+    try:
+        return _Field.apply(*args)
+    finally:
+        _CALLER_GRAD[0] = True
+
+
 class _Field(Function):
     """sdf / grad_x sdf / features / colours at M points, with the analytic (double) backward.
 
@@ -191,8 +203,9 @@ class _Field(Function):
             code = code.contiguous().float() if code is not None else None
         n_rays = view_dirs.shape[0] if use_color else 0
         saved = None
-        # (ctx.needs_input_grad reflects requires_grad even under torch.no_grad(): eval must not save activations)
-        if torch.is_grad_enabled() and any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
+        # (ctx.needs_input_grad reflects requires_grad even under torch.no_grad(), and grad mode is always off INSIDE a
+        # Function's forward: the caller's grad mode is recorded by _apply_field() -- eval must not save activations)
+        if _CALLER_GRAD[0] and any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
             nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), spec.flags)
             # free = what the driver reports plus what torch's caching allocator holds but has not handed out
             free = torch.cuda.mem_get_info(dev)[0]
@@ -383,7 +396,7 @@ class _ImplicitBase(nn.Module):
 
     def _field(self, kind, x, clamp):
         table, offsets = self._table()
-        return _Field.apply(self._field_spec, kind, clamp, self.sphere_scale, 1, x, None, None, table, offsets,
+        return _apply_field(self._field_spec, kind, clamp, self.sphere_scale, 1, x, None, None, table, offsets,
                             *self._flat_weights())
 
     def gradient_sdf(self, x):
@@ -613,7 +626,7 @@ class MonoSDFNetwork(nn.Module):
             code = self.rendering_network.image_code(indices, if_pixel_input)
             table, offsets = inet._table()
             clamp = inet.sdf_bounding_sphere if not self.Grid_MLP else 0.0
-            sdf, grad, _, rgb_flat = _Field.apply(self._render_spec, "render", clamp, inet.sphere_scale, S, points, ray_dirs,
+            sdf, grad, _, rgb_flat = _apply_field(self._render_spec, "render", clamp, inet.sphere_scale, S, points, ray_dirs,
                                                   code, table, offsets, *inet._flat_weights(),
                                                   *self.rendering_network._flat_weights())
             rgb_spec = None
