@@ -161,3 +161,28 @@ def test_bf16_eval_render_close_to_fp32(golden):
     for k in ["rgb_values", "depth_values", "normal_map"]:
         print("REPORT eval %s l2 %.3e max-norm %.3e" % (k, rel_l2(out[k], ref[k]), rel_err(out[k], ref[k])))
         assert rel_err(out[k], ref[k]) < BF16_TOL, (k, rel_err(out[k], ref[k]))
+
+
+def test_training_forward_saves_activations_and_eval_does_not(golden, monkeypatch):
+    """The saved-activation fast path is chosen by the CALLER's grad mode (grad mode is always off inside
+    Function.forward and needs_input_grad ignores no_grad): a training forward acquires a saved buffer, a no_grad forward
+    of the same model must not (it used to, which made chunked eval 2.4x slower)."""
+    from monosdf_b200 import _lib
+    fx = golden("mlp_small")
+    n = fx["n_rays"]
+    model = build_model(fx, DEV)
+    model.set_precision("bf16")
+    rays = _cuda(port.synthetic_rays(n, seed=1))
+    idx = torch.zeros(n, dtype=torch.long, device=DEV)
+    calls = []
+    real = _lib.saved_pool.acquire
+    monkeypatch.setattr(_lib.saved_pool, "acquire", lambda nbytes, dev: (calls.append(nbytes), real(nbytes, dev))[1])
+    model.train()
+    out = model(rays, idx, if_pixel_input=True)
+    assert len(calls) >= 1, "the training forward did not take the saved-activation path"
+    out["rgb_values"].sum().backward()
+    before = len(calls)
+    model.eval()
+    with torch.no_grad():
+        model(rays, idx, if_pixel_input=True)
+    assert len(calls) == before, "a no_grad forward saved activations"
