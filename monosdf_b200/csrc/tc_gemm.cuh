@@ -1,21 +1,22 @@
-// tcgen05 / TMEM / TMA GEMM engine for the MLP sweeps ("bf16 mode" of the field kernels), sm_100a only.
+// tcgen05 / TMEM / TMA GEMM engine for the MLP sweeps (the tensor-core mode of the field kernels), sm_100a only.
 //
-// Two persistent, warp-specialised kernels (1 CTA per SM, 320 threads: TMA producer warp, MMA issuer warp,
-// 8 epilogue warps):
+// Two persistent, warp-specialised kernels, 1 CTA per SM:
 //
-//   k_tc_gemm   C[m, n] = epi( sum_k A[m,k] * W[n,k] )        A [M, K] bf16 K-major (activations),
-//               W [N<=256, K<=320] bf16 K-major: the layer's weights, loaded ONCE per CTA and kept resident in
-//               shared memory while the CTA walks over its 128-row tiles of A (4-stage TMA ring).  Accumulators
-//               live in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of
-//               tile i+1.  Used by the forward / tangent sweeps (W = W_l) and the reverse / backward sweeps
-//               (W = W_l^T, transposed once per step by the weight-prep kernel).
+//   k_tc_gemm   C[m, n] = epi( sum_k A[m,k] * W[n,k] )        A [M, K] 16-bit K-major (activations: fp16, adjoints:
+//               bf16), W [N<=256, K<=320] in A's format, K-major: the layer's weights, loaded ONCE per CTA and kept
+//               resident in shared memory while the CTA walks over its 128-row tiles of A (TMA ring).  Accumulators live
+//               in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//               384 threads = 3 warpgroups: {TMA producer warp, MMA issuer warp, 2 idle} at 40 registers and 8 epilogue
+//               warps at 232 (setmaxnreg).  Used by the forward / tangent sweeps (W = W_l) and the reverse / backward
+//               sweeps (W = W_l^T, transposed once per call by the weight-prep kernel).
 //
-//   k_tc_wgrad  dW[i, j] += sum_m X[m,i] * Y[m,j]             X [M, <=128 per tile], Y [M, <=256] bf16, both
-//               MN-major operands (the contraction runs over the rows = points), split over m across CTAs,
-//               fp32 atomics into dW.
+//   k_tc_wgrad  dW[i, j] += sum_m X[m,i] * Y[m,j]             X [M, <=256 per tile], Y [M, <=256], both MN-major
+//               operands (the contraction runs over the rows = points), split over m across CTAs, fp32 atomics into
+//               dW; 320 threads (producer, MMA issuer, 8 warps that convert the fp16 operand of a mixed-format product
+//               to bf16 in shared memory, sum bias columns and run the epilogue).
 //
-// Shared-memory operand layout is the canonical UMMA SWIZZLE_128B layout written by TMA boxes of 64 bf16 (128 B)
-// inner extent; smem/instruction descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp.
+// Shared-memory operand layout is the canonical UMMA SWIZZLE_128B layout written by TMA boxes of 64 16-bit elements
+// (128 B) inner extent; smem/instruction descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp.
 // Every mbarrier wait carries a clock watchdog that traps instead of hanging the GPU.
 #pragma once
 #include <cuda.h>
