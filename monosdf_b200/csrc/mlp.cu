@@ -11,12 +11,14 @@
 //   backward sweep  pbar_{l-1} = (W_l^T pbar_l)|_h * sigma_{l-1} + z_{l-1}                    (backward only)
 //   weight grads    dW_l += pbar_l^T u_l + a_l^T t_l,  db_l += colsum(pbar_l)
 // where sigma_l = sigmoid(100 p_l) is recovered from the stored post-activation as -expm1(-100 h).
-// Nothing is kept between forward and backward: the backward recomputes the chunk.
+// The library keeps no state: either the caller hands both calls a buffer for the chunk activations (saved mode: the
+// forward leaves h_l, a_l, the colour rows there and the backward reads them back) or the backward recomputes the chunk.
 //
 // The sweeps are written once, generic over the activation element type T:
 //   T = float          fp32 mode: SIMT FFMA GEMMs (gemm_f32.cuh), the reference's arithmetic class (1e-4 parity)
-//   T = __nv_bfloat16  bf16 mode: tcgen05 tensor-core GEMMs with TMEM accumulators and TMA-fed operands
-//                      (tc_gemm.cuh), activations stored in bf16, fp32 accumulation (2e-2 parity)
+//   T = __nv_bfloat16  tensor-core mode: tcgen05 GEMMs with TMEM accumulators and TMA-fed operands (tc_gemm.cuh),
+//                      forward-like matrices stored in fp16, adjoint-like ones in bf16 (Fw<T> below), fp32
+//                      accumulation (2e-2 parity)
 #include <stdlib.h>
 #include <type_traits>
 
