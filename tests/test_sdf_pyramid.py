@@ -63,3 +63,51 @@ def test_surface_volumes_crops():
     assert vol.shape == (128, 128, 128) and vol.dtype.name == "float32"
     assert abs(spacing[0] - 2.0 / 127) < 1e-12 and float(origin[0]) == -1.0
     assert vol[64, 64, 64] < 0 < vol[0, 0, 0]
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir("/root/reference/code"), reason="the reference tree only exists in the build container")
+def test_oracle_pyramid_matches_reference_get_surface_sliding():
+    """The oracle's volume against the one the reference's own utils/plots.py:get_surface_sliding hands to marching cubes
+    (skimage / trimesh / plotly are not installed: stubbed, the marching-cubes stub records its `volume` argument)."""
+    import sys
+    import types
+
+    import numpy as np
+    from oracle import ref_shim
+    ref_shim.load_reference()                     # puts /root/reference/code on sys.path, CPU identity for .cuda()
+    seen = {}
+
+    def marching_cubes(volume, level, spacing):
+        seen["volume"], seen["spacing"] = np.array(volume), spacing
+        return np.zeros((3, 3)), np.zeros((1, 3), dtype=np.int64), np.zeros((3, 3)), np.zeros(3)
+
+    stubs = {"skimage": types.ModuleType("skimage"), "skimage.measure": types.ModuleType("skimage.measure"),
+             "trimesh": types.ModuleType("trimesh"), "trimesh.util": types.ModuleType("trimesh.util"),
+             "termcolor": types.ModuleType("termcolor"), "plotly": types.ModuleType("plotly"),
+             "plotly.graph_objs": types.ModuleType("plotly.graph_objs"), "plotly.offline": types.ModuleType("plotly.offline")}
+    stubs["skimage.measure"].marching_cubes = marching_cubes
+    stubs["skimage"].measure = stubs["skimage.measure"]
+    stubs["trimesh"].Trimesh = lambda *a, **k: ("mesh", a[0])
+    stubs["trimesh.util"].concatenate = lambda meshes: meshes
+    stubs["trimesh"].util = stubs["trimesh.util"]
+    stubs["termcolor"].colored = lambda s, *a, **k: s
+    saved = {k: sys.modules.get(k) for k in stubs}
+    sys.modules.update({k: v for k, v in stubs.items() if k not in sys.modules or k.startswith(("skimage", "trimesh"))})
+    try:
+        sys.modules.pop("utils.plots", None)
+        try:
+            from utils import plots
+        except Exception as e:                     # another missing side import of plots.py: not what is under test
+            pytest.skip("utils.plots does not import here: %r" % (e,))
+        sdf = lambda p: p.norm(dim=-1) - 0.55      # noqa: E731
+        plots.get_surface_sliding("/tmp", 0, sdf, resolution=128, grid_boundary=[-1.0, 1.0], return_mesh=True)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    vol = port.sdf_volume_pyramid(lambda p: p.norm(dim=-1) - 0.55, (-1.0,) * 3, (1.0,) * 3, 128)
+    assert seen["volume"].shape == (128, 128, 128)
+    assert np.array_equal(seen["volume"], vol.numpy().astype(np.float32))          # same torch ops: bit for bit
+    assert seen["spacing"][0] == pytest.approx(2.0 / 127)
