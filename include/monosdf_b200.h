@@ -274,6 +274,13 @@ int msdf_loss_forward_backward(const msdf_loss_desc* desc, int64_t n_rays, int n
 int msdf_tc_selftest(int variant, float* result_host, void* stream);
 int msdf_tc_selftest_count(void);
 
+/* Sdf-only queries of the tensor-core mode (MSDF_MODE_SDF_ONLY + MSDF_FLAG_TENSOR_BF16) run the whole SDF network as ONE
+ * persistent tcgen05 kernel (csrc/fused_mlp.cuh: activations stay in shared / tensor memory; replaces the per-layer
+ * nn.Linear + Softplus chain of network.py:79-96 behind get_sdf_vals :131-137 / :307-309) whenever the geometry allows
+ * it (hidden width 256, PE multires 6 with 0 or 32 grid features).  msdf_set_fused(0) switches back to the per-layer
+ * sweep (A/B measurements, tests); default 1. */
+void msdf_set_fused(int on);
+
 #ifdef __cplusplus
 }
 #endif

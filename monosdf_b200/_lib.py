@@ -77,6 +77,7 @@ _SIGNATURES = {
     "msdf_fused_adam": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_int64, c_float, _P]),
     "msdf_tc_selftest": (c_int, [c_int, POINTER(c_float), _P]),
     "msdf_tc_selftest_count": (c_int, []),
+    "msdf_set_fused": (None, [c_int]),
     "msdf_profile_enable": (c_int, [c_int]),
     "msdf_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int]),
     "msdf_profile_read_bytes": (c_int, [c_int, POINTER(ctypes.c_double)]),

@@ -24,6 +24,7 @@
 
 #include "gemm_f32.cuh"
 #include "tc_gemm.cuh"
+#include "fused_mlp.cuh"
 
 int msdf_hash_forward_rows(const float* x, const float* table, const int* offsets, float* out, int64_t out_ld,
                            int64_t B, int C, int L, float S, uint32_t H, float divide_factor, float* dy_dx, cudaStream_t st);
@@ -1726,12 +1727,85 @@ int make_ctx(Ctx& c, const msdf_mlp_desc* sdf_net, const msdf_encoding_desc* enc
 }
 
 // ----------------------------------------------------------------------------------------------------------
+// sdf-only queries of the tensor-core mode: the whole network in one persistent kernel (fused_mlp.cuh)
+// ----------------------------------------------------------------------------------------------------------
+int g_fused_enabled = [] { const char* e = getenv("MSDF_FUSED"); return e ? atoi(e) : 1; }();   // msdf_set_fused() / MSDF_FUSED=0: A/B switch (fused kernel vs per-layer sweep)
+
+bool fused_applicable(const Ctx& c) {
+    return g_fused_enabled && msdf_fused::fused_supported(c.sn.L, c.sn.in, c.sn.out, c.sn.skip, c.sn.d0, c.pe_w);
+}
+
+int fused_sdf_only(const Ctx& c, const float* x, int64_t M, void* workspace, size_t workspace_bytes, float* sdf, const char* who) {
+    namespace mf = msdf_fused;
+    const Net& n = c.sn;
+    const int L = n.L - 1;
+    const size_t fixed = mf::fused_workspace_bytes(L);
+    const int gw = c.grid ? c.enc->grid_feat_dim : 0;
+    MSDF_CHECK_ARG(sdf != nullptr, "%s: sdf output missing", who);
+    MSDF_CHECK_ARG(workspace_bytes >= fixed + (size_t)gw * 4 * 256, "%s: workspace of %zu bytes is too small for the fused sdf kernel (%zu)",
+                   who, workspace_bytes, fixed + (size_t)gw * 4 * 256);
+    char* ws = (char*)workspace;
+    __half* Wp = reinterpret_cast<__half*>(ws);
+    float* bp = reinterpret_cast<float*>(ws + (size_t)L * 131072);
+    float* wl = bp + (size_t)L * 256;
+    float* hashf = gw > 0 ? reinterpret_cast<float*>(ws + fixed) : nullptr;
+    int64_t chunk = M;
+    if (gw > 0) {
+        const int64_t cap = (int64_t)((workspace_bytes - fixed) / ((size_t)gw * 4)) / 256 * 256;
+        if (chunk > cap) chunk = cap;
+    }
+    mf::PackArgs pa{};
+    mf::Plan P{};
+    pa.L = L; P.L = L;
+    for (int l = 0; l < L; ++l) {
+        pa.W[l] = n.W[l]; pa.b[l] = n.b[l]; pa.out[l] = n.out[l]; pa.in[l] = n.in[l]; pa.ldw[l] = n.ldw[l];
+        pa.scale[l] = l == n.skip ? kInvSqrt2 : 1.0f;
+        P.kb[l] = round_up(n.in[l], 64) / 64;
+    }
+    pa.w_last = n.W[L]; pa.in_last = n.in[L];
+    P.skip_after = n.skip > 0 ? n.skip - 1 : -1;
+    P.bias = bp; P.w_last = wl;
+    P.clamp_radius = c.clamp_radius; P.sphere_scale = c.sphere_scale;
+    const int64_t total = (int64_t)L * 65536 + (int64_t)L * 256 + 256;
+    mf::k_pack_fused<<<nblk(total), 256, 0, c.st>>>(pa, Wp, bp, wl);
+    LAUNCHED("fused weight pack");
+    P.b_last = n.b[L];
+    CUtensorMap mW;
+    RUN(msdf_tc::make_map(&mW, Wp, msdf_tc::kF16, (int64_t)L * 256, 256, 256, 256, who));
+    auto kern = n.d0 == 39 ? mf::k_fused_sdf<39, 39> : mf::k_fused_sdf<39, 71>;
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[n.d0 == 39]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { msdf_set_error("%s: cannot opt in to 227 KB shared memory: %s", who, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
+        attr_set[n.d0 == 39] = true;
+    }
+    const size_t smem = 1024 + 2 * mf::kActBytes + mf::kWStages * mf::kWStageBytes + 1024 + sizeof(mf::FusedBarriers);
+    double kcols = 0.0;
+    for (int l = 0; l < L; ++l) kcols += 64.0 * P.kb[l];
+    for (int64_t m0 = 0; m0 < M; m0 += chunk) {
+        const int64_t Mc = M - m0 < chunk ? M - m0 : chunk;
+        if (gw > 0)
+            RUN(msdf_hash_forward_rows(x + 3 * m0, c.enc->table, c.enc->offsets, hashf, gw, Mc, c.enc->level_dim, c.enc->n_levels,
+                                       c.enc->log2_per_level_scale, (uint32_t)c.enc->base_res, c.enc->divide_factor, nullptr, c.st));
+        const int64_t tiles = (Mc + mf::kTileRows - 1) / mf::kTileRows;
+        const int grid = (int)(tiles < msdf_tc::sm_count() ? tiles : msdf_tc::sm_count());
+        const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)Mc * 256.0 * kcols, c.st, (double)Mc * (16.0 + 4.0 * gw));
+        kern<<<grid, msdf_tc::kGemmThreads, smem, c.st>>>(mW, P, x + 3 * m0, hashf, Mc, sdf + m0);
+        msdf_prof_end(prof, c.st);
+        LAUNCHED("fused sdf network");
+    }
+    return MSDF_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------------
 // forward / backward drivers, generic over T
 // ----------------------------------------------------------------------------------------------------------
 template <class T>
 int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int n_samples, const float* code, int mode,
                   void* workspace, size_t workspace_bytes, float* sdf, float* grad, float* feat, int64_t ld_feat, float* rgb,
                   void* saved, size_t saved_bytes, const char* who) {
+    if constexpr (kIsBf16<T>)
+        if (mode == MSDF_MODE_SDF_ONLY && fused_applicable(c)) return fused_sdf_only(c, x, M, workspace, workspace_bytes, sdf, who);
     const bool saving = saved != nullptr && mode == MSDF_MODE_FORWARD;
     int64_t chunk;
     size_t stride = 0;
@@ -1965,6 +2039,8 @@ extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_enco
     return field_backward<float>(c, x, M, view_dirs, n_samples, code, workspace, workspace_bytes, d_sdf, d_grad, d_feat, ld_dfeat,
                                  rgb, d_rgb, sdf_grads, color_grads, grad_table, d_code, saved, saved_bytes, who);
 }
+
+extern "C" void msdf_set_fused(int on) { g_fused_enabled = on; }
 
 extern "C" int msdf_ray_points(const float* ray_o, const float* ray_d, const float* z, int64_t n_rays, int n, float* points,
                                void* stream) {

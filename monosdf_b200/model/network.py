@@ -191,6 +191,10 @@ class _Field(Function):
         code_per_ray = code is not None and code.shape[0] > 1
         cd_d = spec.color_desc(code_per_ray) if use_color else None
         mode = _lib.MODE_SDF_ONLY if kind == "sdf" else _lib.MODE_FORWARD
+        # the engine is picked ONCE, here: kinds that return the raw feature vector ('forward', 'outputs') run the fp32
+        # engine in every precision mode (msdf_field_forward only has fp32 feature outputs), and so must their saved
+        # activations, workspace and backward
+        flags = spec.flags & ~_lib.FLAG_TENSOR_BF16 if kind in ("forward", "outputs") else spec.flags
         F_dim = spec.sdf_spec.out_dims[-1] - 1
         sdf = torch.empty(M, 1, device=dev) if kind != "gradient" else None
         grad = torch.empty(M, 3, device=dev) if kind in ("outputs", "gradient", "render") else None
@@ -206,7 +210,7 @@ class _Field(Function):
         # (ctx.needs_input_grad reflects requires_grad even under torch.no_grad(), and grad mode is always off INSIDE a
         # Function's forward: the caller's grad mode is recorded by _apply_field() -- eval must not save activations)
         if _CALLER_GRAD[0] and any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
-            nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), spec.flags)
+            nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), flags)
             # free = what the driver reports plus what torch's caching allocator holds but has not handed out
             free = torch.cuda.mem_get_info(dev)[0]
             pooled = sum(t.numel() for t in _lib.saved_pool.free if t.device == dev)
@@ -216,13 +220,14 @@ class _Field(Function):
             if 0 < nbytes <= SAVED_ACTIVATION_FRACTION * (free + pooled):
                 saved = _lib.saved_pool.acquire(nbytes, dev)
         bwd_mode = _lib.MODE_BACKWARD if saved is not None else mode      # the saved layout needs the backward's workspace
-        ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, bwd_mode, spec.flags, dev)
+        ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, bwd_mode, flags, dev)
         _lib.call("msdf_field_forward", sdf_d, enc_d, col_d, cd_d, _lib.ptr(x), M, _lib.ptr(view_dirs) if use_color else None,
                   n_rays, int(n_samples), _lib.ptr(code) if use_color else None, mode, float(clamp_radius), float(sphere_scale),
-                  spec.flags, _lib.ptr(ws), ws.numel(), _lib.ptr(sdf), _lib.ptr(grad), _lib.ptr(feat), F_dim, _lib.ptr(rgb),
+                  flags, _lib.ptr(ws), ws.numel(), _lib.ptr(sdf), _lib.ptr(grad), _lib.ptr(feat), F_dim, _lib.ptr(rgb),
                   _lib.ptr(saved), saved.numel() if saved is not None else 0, _lib.stream())
         ctx.spec, ctx.kind, ctx.clamp, ctx.sphere_scale, ctx.n_samples, ctx.ns = spec, kind, clamp_radius, sphere_scale, n_samples, ns
         ctx.code_per_ray = code_per_ray
+        ctx.flags = flags
         ctx.saved_acts = saved
         ctx.save_for_backward(x, view_dirs if use_color else None, code if use_color else None, table, offsets, rgb, *params)
         return sdf, grad, feat, rgb
@@ -250,7 +255,7 @@ class _Field(Function):
         d_sdf, d_grad, d_feat, d_rgb = c(d_sdf), c(d_grad), c(d_feat), c(d_rgb)
         F_dim = spec.sdf_spec.out_dims[-1] - 1
         n_rays = view_dirs.shape[0] if use_color else 0
-        ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, _lib.MODE_BACKWARD, spec.flags, dev)
+        ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, _lib.MODE_BACKWARD, ctx.flags, dev)
         # the backward consumes (overwrites) the saved activations: a second backward through the same node recomputes.
         # They were laid out for the forward's network (with the colour net for 'render'), so they are only usable
         # when this backward sees the same one.
@@ -259,7 +264,7 @@ class _Field(Function):
         ctx.saved_acts = None
         _lib.call("msdf_field_backward", sdf_d, enc_d, col_d, cd_d, _lib.ptr(x), M, _lib.ptr(view_dirs) if use_color else None,
                   n_rays, int(ctx.n_samples), _lib.ptr(code) if use_color else None, float(ctx.clamp), float(ctx.sphere_scale),
-                  spec.flags, _lib.ptr(ws), ws.numel(), _lib.ptr(d_sdf), _lib.ptr(d_grad), _lib.ptr(d_feat), F_dim,
+                  ctx.flags, _lib.ptr(ws), ws.numel(), _lib.ptr(d_sdf), _lib.ptr(d_grad), _lib.ptr(d_feat), F_dim,
                   _lib.ptr(rgb) if use_color else None, _lib.ptr(d_rgb) if use_color else None, sdf_g, col_g,
                   _lib.ptr(d_table), _lib.ptr(d_code), _lib.ptr(saved), saved.numel() if saved is not None else 0, _lib.stream())
         _lib.saved_pool.release(ctx_saved)

@@ -75,6 +75,12 @@ class FusedAdam:
     def step(self, grad_scale=1.0):
         self.step_count += 1
         a = self.arena
+        # model.to() / .cuda() / .float() after build_optimizer() re-allocates parameter storage: Adam would then update
+        # an arena the model no longer reads
+        for p, (off, k) in zip(a.params, a.slices):
+            if p.data_ptr() != a.flat.data_ptr() + 4 * off:
+                raise RuntimeError("monosdf_b200: a parameter no longer lives in the optimizer's flat arena "
+                                   "(module moved / cast after build_optimizer?)")
         for (lo, hi), lr in zip(a.group_ranges, self.lrs):
             if hi == lo:
                 continue
@@ -84,6 +90,30 @@ class FusedAdam:
 
     def scale_lr(self, factor):
         self.lrs = [lr * factor for lr in self.lrs]
+
+
+class ExponentialLR:
+    """torch.optim.lr_scheduler.ExponentialLR for a FusedAdam (monosdf_train.py:223-226, stepped once per iteration
+    :480): every group's learning rate is multiplied by gamma per step()."""
+
+    def __init__(self, optimizer, gamma):
+        self.optimizer, self.gamma = optimizer, float(gamma)
+        self.last_epoch = 0
+        self.base_lrs = list(optimizer.lrs)
+
+    def step(self):
+        self.last_epoch += 1
+        self.optimizer.scale_lr(self.gamma)
+
+    def get_last_lr(self):
+        return list(self.optimizer.lrs)
+
+    def state_dict(self):
+        return {"gamma": self.gamma, "last_epoch": self.last_epoch, "base_lrs": self.base_lrs, "_last_lr": self.get_last_lr()}
+
+    def load_state_dict(self, sd):
+        self.gamma, self.last_epoch, self.base_lrs = float(sd["gamma"]), int(sd["last_epoch"]), list(sd["base_lrs"])
+        self.optimizer.lrs = list(sd["_last_lr"])
 
 
 def build_optimizer(model, lr=5.0e-4, grid_lr_factor=20.0):
