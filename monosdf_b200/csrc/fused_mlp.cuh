@@ -14,12 +14,18 @@
 //   * weights stream per 64-column k-block (32 KB) through a TMA ring from one packed fp16 matrix (L2 resident, 1 MB);
 //   * the last linear layer (one output row: the sdf) is a dot product in the last hidden layer's epilogue.
 //
-// Softplus(beta = 100): max(v, 0) + log1p(t) / 100 with t = exp(-100 |v|): ONE MUFU (ex2) per element, log1p as a
-// degree-4 polynomial on the FMA pipe (|error| < 7.1e-7 absolute in h, far below fp16 storage resolution) -- the
-// per-layer kernels' ex2 + lg2 version is bound by the XU pipe at 16 results / clk / SM.
+// Arithmetic of the epilogue (the part that bounds the kernel: 32768 activations per 2048-clock MMA pass):
+//   * the network runs in a SCALED domain: activations are stored as c h with c = 100 log2(e), so that the accumulator
+//     holds v' = c (W h + b) and softplus(beta = 100) becomes  c h = max(v', 0) + log2(1 + 2^-|v'|):  one MUFU (ex2 with
+//     free |.| / negate modifiers), a degree-4 polynomial for log2(1 + t) on the FMA pipe, one FMNMX -- no multiply by
+//     100 log2(e), no lg2 (the per-layer kernels' ex2 + lg2 version is bound by the XU pipe at 16 results / clk / SM).
+//     The scale is folded into the packed weights (layer 0 and the skip concat's input columns x c, biases x c, the
+//     last linear layer / c): fp16 rounding is relative, so nothing is lost;
+//   * the bias is not added per element: whoever drains an accumulator chunk writes the NEXT layer's bias into it
+//     (tcgen05.st) and every MMA accumulates.
 //
-// Warp roles (384 threads, setmaxnreg 40 / 232 like k_tc_gemm): warp 0 TMA producer, warp 1 MMA issuer, warps 4-11
-// epilogue (TMEM lane quadrant = warp % 4, the two warps of a quadrant split the 32-column chunks).
+// Warp roles (640 threads, setmaxnreg 40 / 104): warp 0 TMA producer, warp 1 MMA issuer, warps 4-19 epilogue (TMEM lane
+// quadrant = warp % 4; the four warps of a quadrant take 32-column chunks g and g + 4).
 #pragma once
 #include "tc_gemm.cuh"
 
@@ -33,6 +39,9 @@ constexpr uint32_t kWStageBytes = 256u * 128u;      // 256 weight rows x 64 colu
 constexpr uint32_t kKBlockBytes = 128u * 128u;      // 128 rows x 64 columns of one sub-tile's A operand
 constexpr uint32_t kActBytes = 4u * kKBlockBytes;   // 256 columns
 constexpr int kTileRows = 256;
+constexpr int kFusedEpiWarps = 16;
+constexpr int kFusedThreads = (4 + kFusedEpiWarps) * 32;
+constexpr int kFusedRegsLight = 40, kFusedRegsEpi = 104;     // 128 x 40 + 512 x 104 = 58368 <= 640 x 96 (the launch allocation: the pool setmaxnreg draws from)
 
 struct Plan {
     int L;                    // hidden layers = layers run on the tensor core
@@ -50,19 +59,48 @@ struct FusedBarriers {
 };
 
 constexpr float kHalfPi = 1.57079632679489662f;
-constexpr float k100Log2e = 144.26950408889634f;
-// log1p(t) / 100 ~ t (c1 + c2 t + c3 t^2 + c4 t^3) on [0, 1]  (minimax fit, max |error| 7.1e-5 before the / 100)
-constexpr float kC1 = 0.9974489686439758e-2f, kC2 = -0.47130128814472494e-2f, kC3 = 0.225685683948268e-2f, kC4 = -0.05875711578778469e-2f;
+constexpr float kScale = 144.26950408889634f;               // c = 100 log2(e)
+// log2(1 + t) ~ t (c1 + c2 t + ...) on [0, 1]: minimax fits of log1p x log2(e).  Degree 4: max |error| 7.1e-5, degree 3:
+// 5.3e-4 -- in h = (.) / c that is an absolute error of 7.1e-7 / 5.3e-6 against an fp16 storage resolution of 6e-5 at
+// |h| = 0.1 (MSDF_FUSED_POLY selects; one FFMA per element apart)
+#ifndef MSDF_FUSED_POLY
+#define MSDF_FUSED_POLY 3
+#endif
+constexpr float kLog2e = 1.4426950408889634f;
+#if MSDF_FUSED_POLY == 4
+constexpr float kC1 = 0.9974489686439758f * kLog2e, kC2 = -0.47130128814472494f * kLog2e, kC3 = 0.225685683948268f * kLog2e,
+                kC4 = -0.05875711578778469f * kLog2e;
+#else
+constexpr float kC1 = 0.987453191724069f * kLog2e, kC2 = -0.4084068241486968f * kLog2e, kC3 = 0.11463518098588148f * kLog2e;
+#endif
 
 __device__ __forceinline__ float ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
-__device__ __forceinline__ float softplus100_poly(float v) {
-    const float t = ex2f(-fabsf(v) * k100Log2e);
+// c softplus100(v' / c) for the scaled pre-activation v'
+__device__ __forceinline__ float softplus_scaled(float v) {
+    const float t = ex2f(-fabsf(v));
+#if MSDF_FUSED_POLY == 4
     float p = fmaf(kC4, t, kC3);
     p = fmaf(p, t, kC2);
+#else
+    float p = fmaf(kC3, t, kC2);
+#endif
     p = fmaf(p, t, kC1);
     return fmaf(p, t, fmaxf(v, 0.f));
 }
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+          "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+          "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+          "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // column idx (compile time after unrolling) of the encoded input row of the point x:
 // [x, sin(2^0 x), cos(2^0 x), sin(2^1 x), ...] (embedder.py:5-36), then the hash features hf[0 .. kD0 - kPeW) (zeros
@@ -129,7 +167,7 @@ __device__ __forceinline__ void load_hf(const float* __restrict__ hashf, int64_t
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 template <int kPeW, int kD0>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kFusedThreads, 1)
 k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Plan P, const float* __restrict__ x,
             const float* __restrict__ hashf, int64_t M, float* __restrict__ sdf_out) {
     extern __shared__ uint8_t smem_raw[];
@@ -137,8 +175,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sAct = base;                                  // 2 x 64 KB
     const uint32_t sW = sAct + 2u * kActBytes;                   // kWStages x 32 KB
-    const uint32_t sPart = sW + kWStages * kWStageBytes;         // [2][128] floats: half-1 partial dot products
-    FusedBarriers* bars = reinterpret_cast<FusedBarriers*>(gen_base + 2u * kActBytes + kWStages * kWStageBytes + 1024u);
+    FusedBarriers* bars = reinterpret_cast<FusedBarriers*>(gen_base + 2u * kActBytes + kWStages * kWStageBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = (M + kTileRows - 1) / kTileRows;
     const int L = P.L;
@@ -146,7 +183,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < kWStages; ++s) { mbar_init(smem_u32(&bars->wfull[s]), 1); mbar_init(smem_u32(&bars->wempty[s]), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->actready[s]), kEpiWarps); mbar_init(smem_u32(&bars->accfull[s]), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->actready[s]), kFusedEpiWarps); mbar_init(smem_u32(&bars->accfull[s]), 1); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
@@ -156,7 +193,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLight));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kFusedRegsLight));
         if (warp == 0) {
             if (lane == 0) {
                 // ---- TMA producer: the k-blocks of every (layer, sub-tile) pass, in the order the MMA warp consumes them
@@ -174,17 +211,17 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
             __syncwarp();
         } else if (warp == 1) {
             if (lane == 0) {
-                // ---- MMA issuer
+                // ---- MMA issuer.  Every MMA accumulates: the epilogue warps preset the accumulator to the layer's bias.
                 const uint32_t idesc = instr_desc(BM, 256, 0, 0, kF16, kF16);
                 int s = 0; uint32_t ph = 0;
-                uint32_t par[2] = {0u, 0u};
+                uint32_t par0 = 0u, par1 = 0u;
                 for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
                     for (int l = 0; l < L; ++l)
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
-                            // the epilogue has read this sub-tile's accumulator and written layer l's operand
-                            mbar_wait(smem_u32(&bars->actready[sub]), par[sub]);
-                            par[sub] ^= 1u;
+                            // the epilogue has drained this sub-tile's accumulator and written layer l's operand
+                            mbar_wait(smem_u32(&bars->actready[sub]), sub == 0 ? par0 : par1);
+                            if (sub == 0) par0 ^= 1u; else par1 ^= 1u;
                             tc_fence_after();
                             const uint32_t tmem_d = tmem_base + (uint32_t)sub * 256u;
                             const uint32_t act = sAct + (uint32_t)sub * kActBytes;
@@ -196,7 +233,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                                 for (int k = 0; k < BK / UMMA_K; ++k) {
                                     const uint64_t da = smem_desc(act + (uint32_t)kb * kKBlockBytes + k * (UMMA_K * 2), 16, 1024);
                                     const uint64_t db = smem_desc(sW + (uint32_t)s * kWStageBytes + k * (UMMA_K * 2), 16, 1024);
-                                    umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                                    umma_bf16(tmem_d, da, db, idesc, 1u);
                                 }
                                 umma_commit(smem_u32(&bars->wempty[s]));
                                 if (++s == kWStages) { s = 0; ph ^= 1u; }
@@ -207,27 +244,50 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
             __syncwarp();
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-        // ---- epilogue warps
-        const int q = warp & 3, half = (warp - 4) >> 2;
-        const int r = q * 32 + lane;                               // row inside a sub-tile = TMEM lane
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFusedRegsEpi));
+        // ---- epilogue warps: quadrant q = TMEM lanes 32 q .. 32 q + 31 = rows of the sub-tile; group g takes chunks g, g + 4
+        const int q = warp & 3, g = (warp - 4) >> 2;
+        const int r = q * 32 + lane;
         const uint32_t tlane = (uint32_t)(q * 32) << 16;
         constexpr int kNf = kD0 - kPeW;                             // hash features per point (0 or 32)
         constexpr int kKb0 = (kD0 + 63) / 64;
         uint32_t par0 = 0u, par1 = 0u;
+        // this thread's row of the SWIZZLE_128B operand layout: 16-byte piece p of a 128-byte row sits at p ^ (r & 7);
+        // split into the part that depends on the chunk parity (bit 2 of the piece: swhi) and the four low offsets
+        const uint32_t rowoff = (uint32_t)r * 128u, swhi = (uint32_t)(r & 4) << 4;
+        uint32_t swlo[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) swlo[p] = (uint32_t)(p ^ (r & 3)) << 4;
 
-        // encoded input of a sub-tile -> k-blocks 0 .. kKb0-1 of its operand buffer
+        // accumulator chunk `c` of a sub-tile <- the bias of layer l (same 32 values in every row)
+        auto preset_bias = [&](uint32_t tacc, int l, int c) {
+            uint32_t bb[32];
+            const float4* src = reinterpret_cast<const float4*>(P.bias + l * 256 + c * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 t4 = __ldg(src + j);
+                bb[4 * j] = __float_as_uint(t4.x); bb[4 * j + 1] = __float_as_uint(t4.y);
+                bb[4 * j + 2] = __float_as_uint(t4.z); bb[4 * j + 3] = __float_as_uint(t4.w);
+            }
+            tmem_st32(tacc + (uint32_t)c * 32u, bb);
+        };
+        // encoded input of a sub-tile -> k-blocks 0 .. kKb0-1 of its operand buffer; accumulator <- bias of layer 0
         auto produce_input = [&](int sub, const float xv[3], int64_t grow) {
             const uint32_t act = sAct + (uint32_t)sub * kActBytes;
-            float hf[kNf > 0 ? kNf : 1];
-            load_hf<kNf>(hashf, grow, M, hf);
-            uint32_t w[16];
-            if (half == 0) enc_chunk<kPeW, kD0, 0>(xv, hf, w); else enc_chunk<kPeW, kD0, 32>(xv, hf, w);
-            store_chunk(act, r, half, w);
-            if constexpr (kKb0 > 1) {
-                if (half == 0) enc_chunk<kPeW, kD0, 64>(xv, hf, w); else enc_chunk<kPeW, kD0, 96>(xv, hf, w);
-                store_chunk(act, r, 2 + half, w);
+            const uint32_t tacc = tmem_base + tlane + (uint32_t)sub * 256u;
+            preset_bias(tacc, 0, g);
+            preset_bias(tacc, 0, g + 4);
+            if (g < 2 * kKb0) {
+                float hf[kNf > 0 ? kNf : 1];
+                load_hf<kNf>(hashf, grow, M, hf);
+                uint32_t w[16];
+                if (g == 0) enc_chunk<kPeW, kD0, 0>(xv, hf, w);
+                else if (g == 1) enc_chunk<kPeW, kD0, 32>(xv, hf, w);
+                else if (g == 2) enc_chunk<kPeW, kD0, 64>(xv, hf, w);
+                else enc_chunk<kPeW, kD0, 96>(xv, hf, w);
+                store_chunk(act, r, g, w);
             }
+            tmem_st_wait();
             fence_proxy_async();
             tc_fence_before();
             __syncwarp();
@@ -256,77 +316,91 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
             for (int l = 0; l < L; ++l) {
                 const bool last = l == L - 1;
                 const bool skip = l == P.skip_after;
-                const float* __restrict__ bias = P.bias + l * 256 + half * 32;
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     const uint32_t act = sAct + (uint32_t)sub * kActBytes;
-                    const uint32_t tacc = tmem_base + tlane + (uint32_t)sub * 256u + (uint32_t)half * 32u;
+                    const uint32_t tacc = tmem_base + tlane + (uint32_t)sub * 256u;
                     mbar_wait(smem_u32(&bars->accfull[sub]), sub == 0 ? par0 : par1);
                     if (sub == 0) par0 ^= 1u; else par1 ^= 1u;
                     tc_fence_after();
-                    uint32_t acc[2][32];
                     float dot = 0.f;
-                    tmem_ld32_issue(tacc, acc[0]);
-                    // chunks c = half + 2 i, two per iteration (TMEM loads double buffered in registers)
-#pragma unroll 1
-                    for (int ii = 0; ii < 2; ++ii) {
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int i = 2 * ii + k;
-                            const int c = half + 2 * i;
-                            float b[32];
+                    for (int i = 0; i < 2; ++i) {
+                        const int c = g + 4 * i;
+                        // one accumulator chunk at a time (the other three warps of the scheduler hide the TMEM latency);
+                        // the next layer's bias for this chunk is fetched BEFORE the math so that its store never waits
+                        uint32_t acc[32], bb[32];
+                        tmem_ld32_issue(tacc + (uint32_t)c * 32u, acc);
+                        if (!last) {
+                            const float4* src = reinterpret_cast<const float4*>(P.bias + (l + 1) * 256 + c * 32);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 t4 = __ldg(reinterpret_cast<const float4*>(bias + i * 64) + j);
-                                b[4 * j] = t4.x; b[4 * j + 1] = t4.y; b[4 * j + 2] = t4.z; b[4 * j + 3] = t4.w;
+                                const float4 t4 = __ldg(src + j);
+                                bb[4 * j] = __float_as_uint(t4.x); bb[4 * j + 1] = __float_as_uint(t4.y);
+                                bb[4 * j + 2] = __float_as_uint(t4.z); bb[4 * j + 3] = __float_as_uint(t4.w);
                             }
-                            tmem_ld32_wait(acc[k]);
-                            if (i + 1 < 4) tmem_ld32_issue(tacc + (uint32_t)(i + 1) * 64u, acc[k ^ 1]);
-                            float h[32];
+                        }
+                        tmem_ld32_wait(acc);
+                        if (!last) {
+                            if (skip && i == 1) {                            // the skip concat's columns live in chunks 5 .. 7
+                                float h[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) h[j] = softplus100_poly(__uint_as_float(acc[k][j]) + b[j]);
-                            if (!last) {
-                                if (skip && i == 3) {                        // the skip concat's columns: chunks 6 / 7 (kD0 <= 64)
-                                    float hf[kNf > 0 ? kNf : 1];
-                                    load_hf<kNf>(hashf, tile * kTileRows + sub * 128 + r, M, hf);
-                                    if (half == 0) skip_fix<kPeW, kD0, 6>(xc[sub], hf, h); else skip_fix<kPeW, kD0, 7>(xc[sub], hf, h);
-                                }
-                                if constexpr (kD0 > 64) {
-                                    if (skip && i == 2) {                    // ... and 4 / 5 for wider inputs
-                                        float hf[kNf > 0 ? kNf : 1];
-                                        load_hf<kNf>(hashf, tile * kTileRows + sub * 128 + r, M, hf);
-                                        if (half == 0) skip_fix<kPeW, kD0, 4>(xc[sub], hf, h); else skip_fix<kPeW, kD0, 5>(xc[sub], hf, h);
-                                    }
-                                }
+                                for (int j = 0; j < 32; ++j) h[j] = softplus_scaled(__uint_as_float(acc[j]));
+                                float hf[kNf > 0 ? kNf : 1];
+                                load_hf<kNf>(hashf, tile * kTileRows + sub * 128 + r, M, hf);
+                                if (g == 1) skip_fix<kPeW, kD0, 5>(xc[sub], hf, h);
+                                else if (g == 2) skip_fix<kPeW, kD0, 6>(xc[sub], hf, h);
+                                else if (g == 3) skip_fix<kPeW, kD0, 7>(xc[sub], hf, h);
                                 uint32_t w[16];
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) w[j] = pack_h2(h[2 * j], h[2 * j + 1]);
                                 store_chunk(act, r, c, w);
                             } else {
+                                // 8 columns at a time: activation, pack, one 16-byte store into the swizzled operand row
+                                const uint32_t cbase = act + (uint32_t)(c >> 1) * kKBlockBytes + rowoff + ((uint32_t)((c & 1) << 6) ^ swhi);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 t4 = __ldg(reinterpret_cast<const float4*>(P.w_last + c * 32) + j);
-                                    dot = fmaf(h[4 * j], t4.x, dot); dot = fmaf(h[4 * j + 1], t4.y, dot);
-                                    dot = fmaf(h[4 * j + 2], t4.z, dot); dot = fmaf(h[4 * j + 3], t4.w, dot);
+                                for (int p = 0; p < 4; ++p) {
+                                    uint32_t w[4];
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j)
+                                        w[j] = pack_h2(softplus_scaled(__uint_as_float(acc[8 * p + 2 * j])),
+                                                       softplus_scaled(__uint_as_float(acc[8 * p + 2 * j + 1])));
+                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + swlo[p]), "r"(w[0]), "r"(w[1]),
+                                                 "r"(w[2]), "r"(w[3]) : "memory");
                                 }
+                            }
+                            tmem_st32(tacc + (uint32_t)c * 32u, bb);
+                        } else {
+                            const float4* wl4 = reinterpret_cast<const float4*>(P.w_last + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t4 = __ldg(wl4 + j);
+                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j])), t4.x, dot);
+                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 1])), t4.y, dot);
+                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 2])), t4.z, dot);
+                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 3])), t4.w, dot);
                             }
                         }
                     }
                     if (!last) {
+                        tmem_st_wait();
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&bars->actready[sub]));
                     } else {
-                        // sdf = dot over all 256 columns: the two warps of the quadrant combine through shared memory
-                        const uint32_t slot = sPart + (uint32_t)(sub * 128 + r) * 4u;
-                        if (half == 1) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(dot) : "memory");
-                        named_bar_sync(1 + q, 64);
-                        if (half == 0) {
-                            float other;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(other) : "r"(slot) : "memory");
+                        // sdf = dot over all 256 columns: the four warps of the quadrant combine through the tail of the
+                        // sub-tile's operand buffer (free until the next layer-0 epilogue rewrites it)
+                        const uint32_t slot = act + 3u * kKBlockBytes + (uint32_t)(g * 128 + r) * 4u;
+                        if (g != 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(dot) : "memory");
+                        named_bar_sync(1 + q, 128);
+                        if (g == 0) {
+                            float o1, o2, o3;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o1) : "r"(slot + 512u) : "memory");
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o2) : "r"(slot + 1024u) : "memory");
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o3) : "r"(slot + 1536u) : "memory");
                             const int64_t grow = tile * kTileRows + sub * 128 + r;
-                            float sdf = dot + other + __ldg(P.b_last);
+                            float sdf = ((dot + o1) + (o2 + o3)) + __ldg(P.b_last);
                             if (P.clamp_radius > 0.f) {
                                 const float* p3 = xc[sub];
                                 sdf = fminf(sdf, P.sphere_scale * (P.clamp_radius - sqrtf(p3[0] * p3[0] + p3[1] * p3[1] + p3[2] * p3[2])));
@@ -347,11 +421,15 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-// Wp[(l * 256 + r) * 256 + k] = fp16(W_l[r, k] * scale_l), zero padded; bp[l * 256 + r] = b_l[r]; wl[k] = W_last[0, k]
+// Packed parameters of the scaled domain (c = kScale):
+//   Wp[(l * 256 + r) * 256 + k] = fp16(W_l[r, k] * s_l(k)), zero padded; s = c for layer 0 (unscaled input), 1 otherwise;
+//        the skip layer: 1/sqrt2 on the columns of the previous layer's (scaled) output, c/sqrt2 on the input's columns
+//   bp[l * 256 + r] = c b_l[r];   wl[k] = W_last[0, k] / c
 struct PackArgs {
     int L;
     const float* W[kMaxL]; const float* b[kMaxL];
-    int out[kMaxL], in[kMaxL]; int64_t ldw[kMaxL]; float scale[kMaxL];
+    int out[kMaxL], in[kMaxL]; int64_t ldw[kMaxL];
+    int skip, skip_col;                 // skip layer (-1: none) and its first input column
     const float* w_last; int in_last;
 };
 __global__ void k_pack_fused(const __grid_constant__ PackArgs a, __half* __restrict__ Wp, float* __restrict__ bp, float* __restrict__ wl) {
@@ -359,15 +437,17 @@ __global__ void k_pack_fused(const __grid_constant__ PackArgs a, __half* __restr
     const int64_t nW = (int64_t)a.L * 65536;
     if (i < nW) {
         const int l = (int)(i >> 16), r = (int)((i >> 8) & 255), k = (int)(i & 255);
-        const float v = (r < a.out[l] && k < a.in[l]) ? a.W[l][(int64_t)r * a.ldw[l] + k] * a.scale[l] : 0.f;
+        float sc = l == 0 ? kScale : 1.0f;
+        if (l == a.skip) sc = (k < a.skip_col ? 1.0f : kScale) * 0.70710678118654752440f;
+        const float v = (r < a.out[l] && k < a.in[l]) ? a.W[l][(int64_t)r * a.ldw[l] + k] * sc : 0.f;
         Wp[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     } else if (i < nW + (int64_t)a.L * 256) {
         const int64_t t = i - nW;
         const int l = (int)(t >> 8), r = (int)(t & 255);
-        bp[t] = r < a.out[l] ? a.b[l][r] : 0.f;
+        bp[t] = r < a.out[l] ? a.b[l][r] * kScale : 0.f;
     } else if (i < nW + (int64_t)a.L * 256 + 256) {
         const int k = (int)(i - nW - (int64_t)a.L * 256);
-        wl[k] = k < a.in_last ? a.w_last[k] : 0.f;
+        wl[k] = k < a.in_last ? a.w_last[k] / kScale : 0.f;
     }
 }
 

@@ -1759,10 +1759,10 @@ int fused_sdf_only(const Ctx& c, const float* x, int64_t M, void* workspace, siz
     pa.L = L; P.L = L;
     for (int l = 0; l < L; ++l) {
         pa.W[l] = n.W[l]; pa.b[l] = n.b[l]; pa.out[l] = n.out[l]; pa.in[l] = n.in[l]; pa.ldw[l] = n.ldw[l];
-        pa.scale[l] = l == n.skip ? kInvSqrt2 : 1.0f;
         P.kb[l] = round_up(n.in[l], 64) / 64;
     }
     pa.w_last = n.W[L]; pa.in_last = n.in[L];
+    pa.skip = n.skip > 0 ? n.skip : -1; pa.skip_col = n.skip > 0 ? n.out[n.skip - 1] : 0;
     P.skip_after = n.skip > 0 ? n.skip - 1 : -1;
     P.bias = bp; P.w_last = wl;
     P.clamp_radius = c.clamp_radius; P.sphere_scale = c.sphere_scale;
@@ -1779,7 +1779,7 @@ int fused_sdf_only(const Ctx& c, const float* x, int64_t M, void* workspace, siz
         if (e != cudaSuccess) { msdf_set_error("%s: cannot opt in to 227 KB shared memory: %s", who, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
         attr_set[n.d0 == 39] = true;
     }
-    const size_t smem = 1024 + 2 * mf::kActBytes + mf::kWStages * mf::kWStageBytes + 1024 + sizeof(mf::FusedBarriers);
+    const size_t smem = 1024 + 2 * mf::kActBytes + mf::kWStages * mf::kWStageBytes + sizeof(mf::FusedBarriers);
     double kcols = 0.0;
     for (int l = 0; l < L; ++l) kcols += 64.0 * P.kb[l];
     for (int64_t m0 = 0; m0 < M; m0 += chunk) {
@@ -1790,7 +1790,7 @@ int fused_sdf_only(const Ctx& c, const float* x, int64_t M, void* workspace, siz
         const int64_t tiles = (Mc + mf::kTileRows - 1) / mf::kTileRows;
         const int grid = (int)(tiles < msdf_tc::sm_count() ? tiles : msdf_tc::sm_count());
         const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)Mc * 256.0 * kcols, c.st, (double)Mc * (16.0 + 4.0 * gw));
-        kern<<<grid, msdf_tc::kGemmThreads, smem, c.st>>>(mW, P, x + 3 * m0, hashf, Mc, sdf + m0);
+        kern<<<grid, mf::kFusedThreads, smem, c.st>>>(mW, P, x + 3 * m0, hashf, Mc, sdf + m0);
         msdf_prof_end(prof, c.st);
         LAUNCHED("fused sdf network");
     }
