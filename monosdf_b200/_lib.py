@@ -164,14 +164,23 @@ class _SavedPool:
                 best = i
         if best is not None and self.free[best].numel() <= 1.5 * nbytes + (64 << 20):
             return self.free.pop(best)
+        # nothing fits: buffers of other sizes (ragged last batch, eval chunks, another shard size) would only pile up
+        # next to the new one -- hand them back before asking for more
+        self.free = [t for t in self.free if t.device != device]
         return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+    def best_fit_bytes(self, nbytes, device):
+        """size of the pooled buffer acquire() would hand out for this request (0: none) -- the only pooled memory a
+        caller may count as free"""
+        fits = [t.numel() for t in self.free if t.device == device and nbytes <= t.numel() <= 1.5 * nbytes + (64 << 20)]
+        return min(fits) if fits else 0
 
     def release(self, t):
         if t is not None:
             self.free.append(t)
-            if len(self.free) > 8:           # keep the few largest
+            if len(self.free) > 3:           # a step needs two (render + eikonal); keep the largest
                 self.free.sort(key=lambda x: -x.numel())
-                del self.free[8:]
+                del self.free[3:]
 
     def clear(self):
         self.free.clear()

@@ -211,14 +211,16 @@ class _Field(Function):
         # Function's forward: the caller's grad mode is recorded by _apply_field() -- eval must not save activations)
         if _CALLER_GRAD[0] and any(ctx.needs_input_grad) and grad is not None and M > 0 and SAVED_ACTIVATION_FRACTION > 0:
             nbytes = _lib.lib().msdf_field_saved_bytes(sdf_d, enc_d, col_d, cd_d, M, int(n_samples), flags)
-            # free = what the driver reports plus what torch's caching allocator holds but has not handed out
-            free = torch.cuda.mem_get_info(dev)[0]
-            pooled = sum(t.numel() for t in _lib.saved_pool.free if t.device == dev)
-            if not (0 < nbytes <= SAVED_ACTIVATION_FRACTION * (free + pooled)):
-                # second look (slow: builds the allocator's whole statistics dict, 0.15 ms per call)
-                free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-            if 0 < nbytes <= SAVED_ACTIVATION_FRACTION * (free + pooled):
+            # does it fit?  A pooled buffer of the right size is free by construction; otherwise ask the driver, and
+            # only if that says no also count what torch's caching allocator holds but has not handed out (slow query)
+            if _lib.saved_pool.best_fit_bytes(nbytes, dev) > 0:
                 saved = _lib.saved_pool.acquire(nbytes, dev)
+            elif nbytes > 0:
+                free = torch.cuda.mem_get_info(dev)[0] + sum(t.numel() for t in _lib.saved_pool.free if t.device == dev)
+                if nbytes > SAVED_ACTIVATION_FRACTION * free:
+                    free += torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+                if nbytes <= SAVED_ACTIVATION_FRACTION * free:
+                    saved = _lib.saved_pool.acquire(nbytes, dev)
         bwd_mode = _lib.MODE_BACKWARD if saved is not None else mode      # the saved layout needs the backward's workspace
         ws = _workspace_for(sdf_d, enc_d, col_d, cd_d, M, bwd_mode, flags, dev)
         _lib.call("msdf_field_forward", sdf_d, enc_d, col_d, cd_d, _lib.ptr(x), M, _lib.ptr(view_dirs) if use_color else None,

@@ -1,7 +1,7 @@
 """Import shim for the REAL reference (`/root/reference/code`) -- TEST INFRASTRUCTURE ONLY.
 
-Only usable in the build container, where /root/reference exists (it does not
-exist on the GPU box).  Used by oracle/make_golden.py to produce the committed
+Usable in the build container, where /root/reference exists, and on the GPU box through the files
+oracle/stage_reference.py staged under baseline/_ref/.  Used by oracle/make_golden.py to produce the committed
 fixtures under tests/golden/ and by tests that pin oracle/port.py against the
 unmodified reference.  Nothing in monosdf_b200/ may import this file.
 
@@ -18,7 +18,18 @@ import sys
 import types
 import contextlib
 
-REF_ROOT = os.environ.get("MSDF_REFERENCE_ROOT", "/root/reference")
+def _find_root():
+    """/root/reference in the build container; on the GPU box the copy oracle/stage_reference.py left under
+    baseline/_ref/ (git-ignored, travels with the gpurun snapshot)."""
+    cands = [os.environ.get("MSDF_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "code", "model", "network.py")):
+            return c
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 REF_CODE = os.path.join(REF_ROOT, "code")
 
 

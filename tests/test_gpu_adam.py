@@ -2,8 +2,6 @@
 reference trainer's parameter groups (code/training/monosdf_train.py:210-226: hash table lr x20, betas (0.9, 0.99),
 eps 1e-15 for Grid_MLP models; plain Adam(lr) otherwise), including the 1/world gradient scale the all-reduce path
 folds into the step."""
-import copy
-
 import pytest
 import torch
 
@@ -29,7 +27,9 @@ def _reference_optimizer(model, lr, factor):
 def test_fused_adam_matches_torch_adam(golden, case, world):
     fx = golden(case)
     ours = build_model(fx, DEV)
-    ref = copy.deepcopy(ours)
+    ref = build_model(fx, DEV)        # same seed -> identical parameters (weight_norm modules do not deepcopy)
+    for p, q in zip(ours.parameters(), ref.parameters()):
+        assert torch.equal(p, q)
     lr, factor, gamma = 5.0e-4, 20.0, 0.1 ** (1.0 / 50.0)
     arena, opt = training.build_optimizer(ours, lr=lr, grid_lr_factor=factor)
     sched = training.ExponentialLR(opt, gamma)
