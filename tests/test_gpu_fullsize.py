@@ -114,3 +114,35 @@ def test_full_size_training_step_gradients(golden):
     cos = float((a * b).sum() / (a.norm() * b.norm()))
     assert cos > 0.99, cos
     assert abs(float(a.norm() / b.norm()) - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_subsample_matches_oracle(golden, precision):
+    """65 536-ray training forward at the bench's beta = 0.01: a 256-ray subsample of its outputs against the oracle on the
+    SAME sample positions (z_vals injected, like tests/test_gpu_bf16.py) -- values, not just properties, at full size."""
+    from tests.helpers import params_of, rel_err
+    fx = golden("mlp_full")
+    model = build_model(fx, DEV).train()
+    model.set_precision(precision)
+    with torch.no_grad():
+        model.density.beta.fill_(0.01)
+    rays = port.synthetic_rays(N, seed=1)
+    idx = torch.zeros(N, dtype=torch.long, device=DEV)
+    torch.manual_seed(11)
+    with torch.no_grad():
+        out = model(_cuda(rays), idx, if_pixel_input=True)
+    pick = torch.arange(0, N, N // 256)[:256]
+    sub = {k: v[pick] for k, v in rays.items()}
+    params = params_of(model)
+    cfg = port.cfg_from_conf(fx["conf"])
+    out_o = port.model_forward(params, cfg, sub, torch.zeros(256, dtype=torch.long), if_pixel_input=True, training=False,
+                               z_vals=out["z_vals"][pick.to(DEV)].cpu())      # (autograd.grad inside: no no_grad here)
+    tol = 5e-4 if precision == "fp32" else 2e-2
+    for k in ["sdf", "rgb_values", "depth_values", "normal_map"]:
+        e = rel_err(out[k][pick.to(DEV)], out_o[k])
+        print("REPORT full size %s subsample %s %.3e" % (precision, k, e))
+        assert e < tol, (k, e)
+    wa, wb = out["weights"][pick.to(DEV)].double().cpu(), out_o["weights"].double()
+    l2 = float((wa - wb).norm() / wb.norm())
+    print("REPORT full size %s subsample weights l2 %.3e max-norm %.3e" % (precision, l2, rel_err(wa, wb)))
+    assert l2 < tol * (1 if precision == "bf16" else 4)
