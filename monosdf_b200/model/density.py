@@ -33,19 +33,3 @@ class LaplaceDensity(Density):
 
     def get_beta(self):
         return self.beta.abs() + self._beta_min
-
-
-class AbsDensity(Density):
-    def density_func(self, sdf, beta=None):
-        return torch.abs(sdf)
-
-
-class SimpleDensity(Density):
-    def __init__(self, params_init={}, noise_std=1.0):
-        super().__init__(params_init=params_init)
-        self.noise_std = noise_std
-
-    def density_func(self, sdf, beta=None):
-        if self.training and self.noise_std > 0.0:
-            sdf = sdf + torch.randn_like(sdf) * self.noise_std
-        return torch.relu(sdf)

@@ -604,6 +604,10 @@ class MonoSDFNetwork(nn.Module):
             pose = _pose_from_quaternion(pose)
         self._pose_matrix = pose
         B, N = uv.shape[0], uv.shape[1]
+        if B != 1:
+            # the reference breaks here too (depth_scale = ray_dirs_tmp[0] has N rows against B*N rays, network.py:522,555);
+            # fail loudly instead of reading depth_scale out of bounds
+            raise ValueError("monosdf_b200: image (uv) input supports batch size 1, got %d" % B)
         dev = uv.device
         uv, pose, intrinsics = uv.contiguous().float(), pose.contiguous().float(), intrinsics.contiguous().float()
         eye = torch.eye(4, device=dev).repeat(B, 1, 1)

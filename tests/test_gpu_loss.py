@@ -1,11 +1,11 @@
-"""Fused MonoSDFLoss (csrc/loss.cu) against the same loss in torch ops (model/loss.py forward_torch,
+"""Fused MonoSDFLoss (csrc/loss.cu) against the same loss in torch ops (oracle/loss_torch.py forward_torch,
 itself equal to the reference's loss on the golden training fixtures via port.monosdf_loss): the seven scalars and
 the gradients with respect to every renderer output, for every loss variant, masked / unmasked rays and empty masks."""
 import pytest
 import torch
 
 from monosdf_b200.model.loss import MonoSDFLoss
-from oracle import port
+from oracle import loss_torch, port
 from tests.helpers import rel_err
 
 pytestmark = pytest.mark.gpu
@@ -47,7 +47,7 @@ def test_fused_loss_matches_torch(kw, n, fg, gtf, eik):
         dt = torch.float64 if which == "torch" else torch.float32
         o = {k: v.clone().to(DEV, dt).requires_grad_(k != "sdf") for k, v in out.items()}
         g = {k: v.to(DEV, dt) for k, v in gt.items()}
-        r = loss_fn.forward_torch(o, g, True) if which == "torch" else loss_fn(o, g, True)
+        r = loss_torch.forward_torch(loss_fn, o, g, True) if which == "torch" else loss_fn(o, g, True)
         r["loss"].backward()
         res[which] = (r, {k: (v.grad.clone() if v.grad is not None else torch.zeros_like(v)) for k, v in o.items() if k != "sdf"})
     for k in ("loss", "rgb_loss", "eikonal_loss", "smooth_loss", "depth_loss", "normal_l1", "normal_cos"):

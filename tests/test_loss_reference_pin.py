@@ -1,4 +1,4 @@
-"""CPU: the loss oracle (oracle/port.py:monosdf_loss) and the host module's torch path (MonoSDFLoss.forward_torch) against
+"""CPU: the loss oracle (oracle/port.py:monosdf_loss) and the host module's torch path (oracle/loss_torch.py) against
 the REFERENCE's own model/loss.py:MonoSDFLoss on the reference's model outputs stored in the golden fixtures -- pins
 SURVEY section 8 row f1 by execution.  (The fused CUDA loss is compared with forward_torch in tests/test_gpu_loss.py.)"""
 import os
@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-from oracle import port
+from oracle import loss_torch, port
 
 REF = "/root/reference/code"
 pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason="the reference tree only exists in the build container")
@@ -35,7 +35,7 @@ def test_loss_oracle_and_host_module_match_reference_loss(golden, case, masked):
     ref = _reference_loss()(out, {k: v.clone() for k, v in gt.items()}, if_pixel_input=True)
     ours = port.monosdf_loss(out, gt)
     from monosdf_b200.model.loss import MonoSDFLoss
-    host = MonoSDFLoss().forward_torch(out, gt, if_pixel_input=True)
+    host = loss_torch.forward_torch(MonoSDFLoss(), out, gt, if_pixel_input=True)
     for k in KEYS:
         r = float(ref[k])
         assert float(ours[k]) == pytest.approx(r, rel=1e-6, abs=1e-9), (k, "oracle")
