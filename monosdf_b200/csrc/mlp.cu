@@ -750,6 +750,13 @@ struct EpiAtomic : EpiBase<EpiAtomic> {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
         const EpiAtomic e = *this;
+        if (nv == 32 && col_rot == 0 && (ldc & 3) == 0 && (n0 & 3) == 0 && ((reinterpret_cast<uintptr_t>(C) & 15) == 0)) {
+            io.atomic_add_v4(v, (int64_t)Mrows, [=](int64_t m) -> float* {
+                const int64_t r = e.perm_rows > 0 ? (m + e.perm_shift) % e.perm_rows : m;
+                return e.C + r * e.ldc + n0;
+            });
+            return;
+        }
         io.atomic_add(v, (int64_t)Mrows, [=](int64_t m, int c) -> float* {
             if (c >= nv) return nullptr;
             const int64_t r = e.perm_rows > 0 ? (m + e.perm_shift) % e.perm_rows : m;
