@@ -10,9 +10,10 @@
 // Entry points mirror hashencoder.h:13-15 with raw device pointers instead of at::Tensor.
 //
 // B200 layout decisions (differences from the reference's launch shape, not its results):
-//   * one thread per POINT looping over levels (the whole 46.5 MB table is L2-resident on B200, so the
-//     reference's level-major grid "so one level fits cache" buys nothing); x is read once, the 128 B feature
-//     row of a point is written by one thread, gathers are 8-byte float2 loads with 8 independent loads in flight;
+//   * one thread per (POINT, LEVEL), level fastest (the whole 46.5 MB table is L2-resident on B200, so the
+//     reference's level-major grid "so one level fits cache" buys nothing): a warp holds two points x 16 levels, all
+//     128 gathers of a point are in flight at once (8-byte float2 loads), and the 128 B feature row / 384 B dy_dx row
+//     of a point leave the warp as contiguous runs;
 //   * scatters use 8-byte vector atomics (red.global.add.v2.f32) into the L2-resident gradient table.
 // All three kernels are HBM/L2-gather bound; algorithmic bytes per point are listed in DESIGN.md.
 #include "common.cuh"
@@ -38,7 +39,10 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
     if (stride <= hashmap_size) { index += y * stride; stride *= res; }
     if (stride <= hashmap_size) { index += z * stride; stride *= res; }
     if (stride > hashmap_size) index = x ^ (y * kPrimeY) ^ (z * kPrimeZ);
-    return index % hashmap_size;
+    // index % hashmap_size without the ~20-instruction integer division where it can be avoided: hashed levels have a
+    // power-of-two size (a mask), dense levels only wrap for the corner coordinate that equals res (a rare branch)
+    if ((hashmap_size & (hashmap_size - 1u)) == 0u) return index & (hashmap_size - 1u);
+    return index < hashmap_size ? index : index % hashmap_size;
 }
 
 __device__ __forceinline__ bool load_point(const float* __restrict__ x, int64_t b, float divide_factor, float p[3]) {
@@ -98,73 +102,83 @@ __device__ __forceinline__ void atomic_add_feat(float* t, uint32_t idx, const fl
 
 // outputs: level_major ? [L,B,C] : row b at out + b*out_ld, feature (l*C + c)
 // dy_dx  : [B, L, 3, C] (hashencoder.cu:212)
+// One thread per (point, level), level fastest: a warp covers 32 / L points x all L levels, so that ALL the gathers of
+// a point (L x 8 corners) are in flight at once instead of 8 at a time (the thread-per-point form walked the levels
+// serially: 296 us for 262144 points, 14 % of the issue slots busy), and a point's feature row / dy_dx row leaves the
+// warp as one contiguous run (L*C floats: lane l writes features l*C .. l*C+C-1).
 template <int C>
 __global__ void __launch_bounds__(256)
 k_hash_forward(const float* __restrict__ x, const float* __restrict__ table, const int* __restrict__ offsets,
                float* __restrict__ out, int64_t out_ld, int level_major, int64_t B, int L, float S, uint32_t H,
                float divide_factor, float* __restrict__ dy_dx) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = gid / L;
+    const int l = (int)(gid - b * L);
     if (b >= B) return;
     float p[3];
     const bool oob = load_point(x, b, divide_factor, p);
-    for (int l = 0; l < L; ++l) {
-        float res[C];
-        float grad[3][C];
+    float res[C];
+    float grad[3][C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) { res[c] = 0.0f; grad[0][c] = grad[1][c] = grad[2][c] = 0.0f; }
-        if (!oob) {
-            const LevelGeom g = level_geom(offsets, l, S, H);
-            const float* t = table + (size_t)offsets[l] * C;
-            const Cell cell = make_cell(p, g.scale);
-            float v[8][C];
+    for (int c = 0; c < C; ++c) { res[c] = 0.0f; grad[0][c] = grad[1][c] = grad[2][c] = 0.0f; }
+    if (!oob) {
+        const LevelGeom g = level_geom(offsets, l, S, H);
+        const float* t = table + (size_t)offsets[l] * C;
+        const Cell cell = make_cell(p, g.scale);
+        float v[8][C];
 #pragma unroll
-            for (int idx = 0; idx < 8; ++idx) {
-                uint32_t gi = grid_index(cell.g[0] + (idx & 1), cell.g[1] + ((idx >> 1) & 1), cell.g[2] + ((idx >> 2) & 1),
-                                         g.hashmap_size, g.res);
-                load_feat<C>(t, gi, v[idx]);
-            }
+        for (int idx = 0; idx < 8; ++idx) {
+            uint32_t gi = grid_index(cell.g[0] + (idx & 1), cell.g[1] + ((idx >> 1) & 1), cell.g[2] + ((idx >> 2) & 1),
+                                     g.hashmap_size, g.res);
+            load_feat<C>(t, gi, v[idx]);
+        }
 #pragma unroll
-            for (int idx = 0; idx < 8; ++idx) {
-                float w = 1.0f;
+        for (int idx = 0; idx < 8; ++idx) {
+            float w = 1.0f;
 #pragma unroll
-                for (int d = 0; d < 3; ++d) w *= ((idx >> d) & 1) ? cell.w1[d] : 1.0f - cell.w1[d];
+            for (int d = 0; d < 3; ++d) w *= ((idx >> d) & 1) ? cell.w1[d] : 1.0f - cell.w1[d];
 #pragma unroll
-                for (int c = 0; c < C; ++c) res[c] += w * v[idx][c];
-            }
-            if (dy_dx != nullptr) {
+            for (int c = 0; c < C; ++c) res[c] += w * v[idx][c];
+        }
+        if (dy_dx != nullptr) {
 #pragma unroll
-                for (int gd = 0; gd < 3; ++gd) {
+            for (int gd = 0; gd < 3; ++gd) {
 #pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        float w = g.scale;
-                        int base = 0;
+                for (int sub = 0; sub < 4; ++sub) {
+                    float w = g.scale;
+                    int base = 0;
 #pragma unroll
-                        for (int nd = 0; nd < 2; ++nd) {
-                            const int d = (nd >= gd) ? nd + 1 : nd;
-                            const int bit = (sub >> nd) & 1;
-                            w *= bit ? cell.w1[d] : 1.0f - cell.w1[d];
-                            base |= bit << d;
-                        }
-#pragma unroll
-                        for (int c = 0; c < C; ++c)
-                            grad[gd][c] += w * (v[base | (1 << gd)][c] - v[base][c]) * cell.dw[gd];
+                    for (int nd = 0; nd < 2; ++nd) {
+                        const int d = (nd >= gd) ? nd + 1 : nd;
+                        const int bit = (sub >> nd) & 1;
+                        w *= bit ? cell.w1[d] : 1.0f - cell.w1[d];
+                        base |= bit << d;
                     }
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        grad[gd][c] += w * (v[base | (1 << gd)][c] - v[base][c]) * cell.dw[gd];
                 }
             }
         }
-        if (level_major) {
+    }
+    float* o = level_major ? out + ((int64_t)l * B + b) * C : out + b * out_ld + l * C;
+    if constexpr (C == 2) {
+        if ((reinterpret_cast<uintptr_t>(o) & 7) == 0) *reinterpret_cast<float2*>(o) = make_float2(res[0], res[1]);
+        else { o[0] = res[0]; o[1] = res[1]; }
+    } else {
 #pragma unroll
-            for (int c = 0; c < C; ++c) out[((int64_t)l * B + b) * C + c] = res[c];
+        for (int c = 0; c < C; ++c) o[c] = res[c];
+    }
+    if (dy_dx != nullptr) {
+        float* od = dy_dx + ((b * L + l) * 3) * C;
+        if constexpr (C == 2) {       // 24 bytes per (point, level), 8-byte aligned: three vector stores
+#pragma unroll
+            for (int gd = 0; gd < 3; ++gd) *reinterpret_cast<float2*>(od + gd * 2) = make_float2(grad[gd][0], grad[gd][1]);
         } else {
-#pragma unroll
-            for (int c = 0; c < C; ++c) out[b * out_ld + l * C + c] = res[c];
-        }
-        if (dy_dx != nullptr) {
-            float* o = dy_dx + ((b * L + l) * 3) * C;
 #pragma unroll
             for (int gd = 0; gd < 3; ++gd)
 #pragma unroll
-                for (int c = 0; c < C; ++c) o[gd * C + c] = grad[gd][c];
+                for (int c = 0; c < C; ++c) od[gd * C + c] = grad[gd][c];
         }
     }
 }
@@ -182,7 +196,11 @@ k_hash_scatter(const float* __restrict__ x, const int* __restrict__ offsets, int
                const float* __restrict__ grad2, int64_t grad2_ld, int grad2_level_major,
                const float* __restrict__ gg_x, float gg_scale,
                float* __restrict__ grad_table) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per (point, level), level fastest (see k_hash_forward): the gradient row of a point is read as one
+    // contiguous run by the warp and all L x 8 vector reductions of a point are issued at once
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t b = gid / L;
+    const int l = (int)(gid - b * L);
     if (b >= B) return;
     float p[3];
     if (load_point(x, b, divide_factor, p)) return;   // grad table is pre-zeroed by the caller (:285)
@@ -191,41 +209,39 @@ k_hash_scatter(const float* __restrict__ x, const int* __restrict__ offsets, int
 #pragma unroll
         for (int d = 0; d < 3; ++d) ggx[d] = gg_x[b * 3 + d] * gg_scale;
     }
-    for (int l = 0; l < L; ++l) {
-        const LevelGeom g = level_geom(offsets, l, S, H);
-        const Cell cell = make_cell(p, g.scale);
-        float g1[C], g2[C];
+    const LevelGeom g = level_geom(offsets, l, S, H);
+    const Cell cell = make_cell(p, g.scale);
+    float g1[C], g2[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            g1[c] = grad ? (grad_level_major ? grad[((int64_t)l * B + b) * C + c] : grad[b * grad_ld + l * C + c]) : 0.0f;
-            g2[c] = (gg_x && grad2) ? (grad2_level_major ? grad2[((int64_t)l * B + b) * C + c] : grad2[b * grad2_ld + l * C + c]) : 0.0f;
-        }
-        float* t = grad_table + (size_t)offsets[l] * C;
+    for (int c = 0; c < C; ++c) {
+        g1[c] = grad ? (grad_level_major ? grad[((int64_t)l * B + b) * C + c] : grad[b * grad_ld + l * C + c]) : 0.0f;
+        g2[c] = (gg_x && grad2) ? (grad2_level_major ? grad2[((int64_t)l * B + b) * C + c] : grad2[b * grad2_ld + l * C + c]) : 0.0f;
+    }
+    float* t = grad_table + (size_t)offsets[l] * C;
 #pragma unroll
-        for (int idx = 0; idx < 8; ++idx) {
-            float w = 1.0f;
+    for (int idx = 0; idx < 8; ++idx) {
+        float w = 1.0f;
 #pragma unroll
-            for (int d = 0; d < 3; ++d) w *= ((idx >> d) & 1) ? cell.w1[d] : 1.0f - cell.w1[d];
-            // d(w)/d(x01_d) * gg_x[d] summed over d
-            float wd = 0.0f;
-            if (gg_x != nullptr) {
+        for (int d = 0; d < 3; ++d) w *= ((idx >> d) & 1) ? cell.w1[d] : 1.0f - cell.w1[d];
+        // d(w)/d(x01_d) * gg_x[d] summed over d
+        float wd = 0.0f;
+        if (gg_x != nullptr) {
 #pragma unroll
-                for (int gd = 0; gd < 3; ++gd) {
-                    float wo = g.scale;
+            for (int gd = 0; gd < 3; ++gd) {
+                float wo = g.scale;
 #pragma unroll
-                    for (int d = 0; d < 3; ++d)
-                        if (d != gd) wo *= ((idx >> d) & 1) ? cell.w1[d] : 1.0f - cell.w1[d];
-                    const float sgn = ((idx >> gd) & 1) ? 1.0f : -1.0f;
-                    wd += sgn * wo * cell.dw[gd] * ggx[gd];
-                }
+                for (int d = 0; d < 3; ++d)
+                    if (d != gd) wo *= ((idx >> d) & 1) ? cell.w1[d] : 1.0f - cell.w1[d];
+                const float sgn = ((idx >> gd) & 1) ? 1.0f : -1.0f;
+                wd += sgn * wo * cell.dw[gd] * ggx[gd];
             }
-            float val[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) val[c] = w * g1[c] + wd * g2[c];
-            const uint32_t gi = grid_index(cell.g[0] + (idx & 1), cell.g[1] + ((idx >> 1) & 1), cell.g[2] + ((idx >> 2) & 1),
-                                           g.hashmap_size, g.res);
-            atomic_add_feat<C>(t, gi, val);
         }
+        float val[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) val[c] = w * g1[c] + wd * g2[c];
+        const uint32_t gi = grid_index(cell.g[0] + (idx & 1), cell.g[1] + ((idx >> 1) & 1), cell.g[2] + ((idx >> 2) & 1),
+                                       g.hashmap_size, g.res);
+        atomic_add_feat<C>(t, gi, val);
     }
 }
 
@@ -266,7 +282,7 @@ int launch_forward(const float* x, const float* table, const int* offsets, float
                    int64_t B, int L, float S, uint32_t H, float divide_factor, float* dy_dx, cudaStream_t st) {
     // algorithmic bytes per point: 12 (x) + L*8 corners*C*4 (gathers) + L*C*4 (features) (+ L*3*C*4 when dy_dx is materialised)
     const int prof = msdf_prof_begin(MSDF_PROF_HASH, 0.0, st, (double)B * (12.0 + L * C * 4.0 * 9.0 + (dy_dx ? L * C * 12.0 : 0.0)));
-    k_hash_forward<C><<<(unsigned)msdf_div_up(B, 256), 256, 0, st>>>(x, table, offsets, out, out_ld, level_major, B, L, S, H,
+    k_hash_forward<C><<<(unsigned)msdf_div_up(B * L, 256), 256, 0, st>>>(x, table, offsets, out, out_ld, level_major, B, L, S, H,
                                                                     divide_factor, dy_dx);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
@@ -280,7 +296,7 @@ int launch_scatter(const float* x, const int* offsets, int64_t B, int L, float S
                    const float* gg_x, float gg_scale, float* grad_table, cudaStream_t st) {
     // per point: 12 (x) + L*C*4 (grad) + L*8*C*4*2 (read-modify-write of the gradient table)
     const int prof = msdf_prof_begin(MSDF_PROF_HASH, 0.0, st, (double)B * (12.0 + L * C * 4.0 * (grad2 ? 2.0 : 1.0) + L * C * 64.0));
-    k_hash_scatter<C><<<(unsigned)msdf_div_up(B, 256), 256, 0, st>>>(x, offsets, B, L, S, H, divide_factor, grad, grad_ld, glm,
+    k_hash_scatter<C><<<(unsigned)msdf_div_up(B * L, 256), 256, 0, st>>>(x, offsets, B, L, S, H, divide_factor, grad, grad_ld, glm,
                                                                     grad2, grad2_ld, g2lm, gg_x, gg_scale, grad_table);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
