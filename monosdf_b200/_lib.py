@@ -131,7 +131,29 @@ def ptr(t):
 
 
 def stream():
-    return torch.cuda.current_stream().cuda_stream
+    """Raw handle of torch's CURRENT stream (torch.cuda.current_stream() builds a Python Stream object: 15 us per call,
+    a third of a millisecond per 1024-ray eval chunk; the raw getter is the one Triton's launcher uses)."""
+    try:
+        return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+    except AttributeError:      # pragma: no cover  (older / newer torch without the private getter)
+        return torch.cuda.current_stream().cuda_stream
+
+
+# bumped by everything that rewrites parameter memory behind autograd's back (training.FusedAdam.step: a raw kernel on the
+# flat arena does not touch the tensors' version counters); part of the key of the effective-weight cache
+param_epoch = [0]
+
+_consts = {}
+
+
+def device_constant(key, device, make):
+    """Small constant tensors the host loops re-create every call (linspace grids ...), made once per device."""
+    k = (key, device.type, device.index)
+    t = _consts.get(k)
+    if t is None:
+        t = make().to(device)
+        _consts[k] = t
+    return t
 
 
 _workspaces = {}

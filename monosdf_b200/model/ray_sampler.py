@@ -41,7 +41,7 @@ class UniformSampler(RaySampler):
 
     def _init(self, ray_dirs, cam_loc, training, cap, beta_coef=0.0):
         N, n0, dev = ray_dirs.shape[0], self.N_samples, ray_dirs.device
-        t_vals = torch.linspace(0.0, 1.0, steps=n0).to(dev)
+        t_vals = _lib.device_constant(("linspace01", n0), dev, lambda: torch.linspace(0.0, 1.0, steps=n0))
         t_rand = _rand((N, n0), dev, self.rng).contiguous() if training else None
         z = torch.empty(N, cap, device=dev)
         beta = torch.empty(N, device=dev)
@@ -101,7 +101,7 @@ class ErrorBoundSampler(RaySampler):
                 not_converge = iters < self.max_total_iters and bool(flag.item())
                 if not not_converge:
                     break
-                u = torch.linspace(0.0, 1.0, steps=n0).to(dev)
+                u = _lib.device_constant(("linspace01", n0), dev, lambda: torch.linspace(0.0, 1.0, steps=n0))
                 z_new = torch.empty(N, n0, device=dev)
                 pts = torch.empty(N * n0, 3, device=dev)
                 _lib.call("msdf_sampler_upsample", N, n, _lib.ptr(z), _lib.ptr(sdf), cap, _lib.ptr(beta), float(self.add_tiny),
@@ -114,14 +114,15 @@ class ErrorBoundSampler(RaySampler):
                 u = _rand((N, ns), dev, self.rng).contiguous()
                 per_ray = 1
             else:
-                u = torch.linspace(0.0, 1.0, steps=ns).to(dev)
+                u = _lib.device_constant(("linspace01", ns), dev, lambda: torch.linspace(0.0, 1.0, steps=ns))
                 per_ray = 0
             if self.N_samples_extra > 0:
                 if training:
                     pick = torch.randperm(n)[: self.N_samples_extra] if self.rng == "reference" else \
                         torch.randperm(n, device=dev)[: self.N_samples_extra]
                 else:
-                    pick = torch.linspace(0, n - 1, self.N_samples_extra).long()
+                    ne = self.N_samples_extra
+                    pick = _lib.device_constant(("pick", n, ne), dev, lambda: torch.linspace(0, n - 1, ne).long().to(torch.int32))
                 pick = pick.to(device=dev, dtype=torch.int32).contiguous()
             else:
                 pick = None

@@ -74,6 +74,7 @@ class FusedAdam:
 
     def step(self, grad_scale=1.0):
         self.step_count += 1
+        _lib.param_epoch[0] += 1          # parameter memory changes without the tensors' version counters noticing
         a = self.arena
         # model.to() / .cuda() / .float() after build_optimizer() re-allocates parameter storage: Adam would then update
         # an arena the model no longer reads

@@ -111,3 +111,33 @@ def test_fused_kernel_is_what_runs():
     _sdf(model, x, "bf16", False)
     sweep_launches = _lib.launch_count() - before
     assert fused_launches < sweep_launches and fused_launches <= 12, (fused_launches, sweep_launches)
+
+
+def test_effective_weight_cache_follows_parameter_updates(golden):
+    """no-grad calls reuse the weight-normed weights while nothing changed, and see every kind of update: in-place torch
+    ops (version counters), load_state_dict, and the fused Adam kernel that writes the flat arena directly."""
+    from monosdf_b200 import training
+    from oracle import port
+    fx = golden("mlp_small")
+    model = build_model(fx, DEV).eval()
+    x = _points(2000, seed=2, spread=0.6)
+    with torch.no_grad():
+        a = model.implicit_network.get_sdf_vals(x).clone()
+        b = model.implicit_network.get_sdf_vals(x).clone()
+        assert torch.equal(a, b)
+        model.implicit_network.lin1.weight_g.mul_(1.5)                       # in-place update
+        c = model.implicit_network.get_sdf_vals(x).clone()
+    assert not torch.equal(a, c)
+    arena, opt = training.build_optimizer(model)
+    arena.zero_grad()
+    for p in model.parameters():
+        p.grad.fill_(1.0e-2)
+    opt.step()                                                              # raw kernel on the arena
+    with torch.no_grad():
+        d = model.implicit_network.get_sdf_vals(x).clone()
+    assert not torch.equal(c, d)
+    model2 = build_model(fx, DEV).eval()
+    model2.load_state_dict(model.state_dict(), strict=True)
+    with torch.no_grad():
+        e = model2.implicit_network.get_sdf_vals(x).clone()
+    assert torch.equal(d, e)
