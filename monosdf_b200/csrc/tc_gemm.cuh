@@ -468,7 +468,7 @@ struct WarpIO {
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot + (uint32_t)(lane * 128 + (((c ^ lane) & 31) << 2))), "f"(v[c]) : "memory");
         __syncwarp();
         const bool on = lane >= jlo && lane < jhi;
-#pragma unroll 1
+#pragma unroll 4
         for (int r = 0; r < rows_left; ++r) {
             float x;
             asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(slot + (uint32_t)(r * 128 + (((lane ^ r) & 31) << 2))) : "memory");
