@@ -51,12 +51,21 @@ struct Plan {
     const float* w_last;      // [256]: the sdf row of the last linear layer (zero padded)
     const float* b_last;      // its bias (device scalar)
     float clamp_radius, sphere_scale;   // get_sdf_vals' bounding-sphere clamp (network.py:134-136); radius <= 0: none
+    // training forward (kTrain): the stored activation of layer l is scaled by oscale[l] (1/sqrt2 for the skip concat,
+    // network.py:88-89: the convention of the per-layer sweeps that read the saved matrices back)
+    float oscale[kMaxL];
+    __half* feat; int64_t ldfeat;       // feature head output rows (the colour net's input, fp16), may be null
 };
+
+struct StoreMaps { CUtensorMap m[kMaxL + 1]; };     // kTrain: H[l], the saved input of layer l (TMA stores of the operand tiles)
+
 
 struct FusedBarriers {
     uint64_t wfull[kWStages], wempty[kWStages], actready[2], accfull[2];
     uint32_t tmem_base, pad;
 };
+static_assert(sizeof(FusedBarriers) <= 128, "the partial-sum slots start 128 bytes behind the barriers");
+constexpr uint32_t kFusedTailBytes = 128u + 3u * 128u * 4u;          // barriers + partial sdf sums
 
 constexpr float kHalfPi = 1.57079632679489662f;
 constexpr float kScale = 144.26950408889634f;               // c = 100 log2(e)
@@ -88,6 +97,27 @@ __device__ __forceinline__ float softplus_scaled(float v) {
     p = fmaf(p, t, kC1);
     return fmaf(p, t, fmaxf(v, 0.f));
 }
+
+// softplus100(v) for the UNSCALED pre-activation (training forward: the saved activations keep the per-layer sweeps' units)
+__device__ __forceinline__ float softplus_plain(float v) {
+    constexpr float k = 1.0f / kScale;
+    const float t = ex2f(-fabsf(v) * kScale);
+#if MSDF_FUSED_POLY == 4
+    float p = fmaf(kC4 * k, t, kC3 * k);
+    p = fmaf(p, t, kC2 * k);
+#else
+    float p = fmaf(kC3 * k, t, kC2 * k);
+#endif
+    p = fmaf(p, t, kC1 * k);
+    return fmaf(p, t, fmaxf(v, 0.f));
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
     asm volatile(
@@ -166,19 +196,26 @@ __device__ __forceinline__ void load_hf(const float* __restrict__ hashf, int64_t
 
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-template <int kPeW, int kD0>
+// kTrain = false: sdf-only queries (scaled domain, nothing stored but the sdf).
+// kTrain = true : the forward sweep of a training / rendering step: plain units, every layer's input H[l] leaves the SM
+//                 ONCE, as TMA stores of the operand tiles the MMAs read anyway (write-only saved activations), plus one
+//                 more tensor-core layer for the feature head (rows 1.. of the last linear layer) whose rows go straight
+//                 into the colour net's input matrix; sdf_out receives the raw sdf (the decode kernel clamps).
+template <int kPeW, int kD0, bool kTrain>
 __global__ void __launch_bounds__(kFusedThreads, 1)
-k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Plan P, const float* __restrict__ x,
-            const float* __restrict__ hashf, int64_t M, float* __restrict__ sdf_out) {
+k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Plan P, const __grid_constant__ StoreMaps SM,
+            const float* __restrict__ x, const float* __restrict__ hashf, int64_t M, float* __restrict__ sdf_out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t sAct = base;                                  // 2 x 64 KB
     const uint32_t sW = sAct + 2u * kActBytes;                   // kWStages x 32 KB
     FusedBarriers* bars = reinterpret_cast<FusedBarriers*>(gen_base + 2u * kActBytes + kWStages * kWStageBytes);
+    const uint32_t sPart = sW + kWStages * kWStageBytes + 128u;  // [3 groups][128 rows] partial sdf sums
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = (M + kTileRows - 1) / kTileRows;
     const int L = P.L;
+    const int LT = kTrain ? L + 1 : L;                           // tensor-core layers: + the feature head when training
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapW);
@@ -199,7 +236,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                 // ---- TMA producer: the k-blocks of every (layer, sub-tile) pass, in the order the MMA warp consumes them
                 int s = 0; uint32_t ph = 0;
                 for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                    for (int l = 0; l < L; ++l)
+                    for (int l = 0; l < LT; ++l)
                         for (int sub = 0; sub < 2; ++sub)
                             for (int kb = 0; kb < P.kb[l]; ++kb) {
                                 mbar_wait(smem_u32(&bars->wempty[s]), ph ^ 1u);
@@ -216,7 +253,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                 int s = 0; uint32_t ph = 0;
                 uint32_t par0 = 0u, par1 = 0u;
                 for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
-                    for (int l = 0; l < L; ++l)
+                    for (int l = 0; l < LT; ++l)
 #pragma unroll
                         for (int sub = 0; sub < 2; ++sub) {
                             // the epilogue has drained this sub-tile's accumulator and written layer l's operand
@@ -226,6 +263,12 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                             const uint32_t tmem_d = tmem_base + (uint32_t)sub * 256u;
                             const uint32_t act = sAct + (uint32_t)sub * kActBytes;
                             const int nkb = P.kb[l];
+                            if constexpr (kTrain) {
+                                // H[l] <- the operand tile (the epilogue warps fenced their writes for the async proxy)
+                                const int row = (int)(tile * kTileRows + sub * 128);
+                                for (int kb = 0; kb < nkb; ++kb) tma_store_2d(&SM.m[l], act + (uint32_t)kb * kKBlockBytes, kb * BK, row);
+                                tma_store_commit();
+                            }
                             for (int kb = 0; kb < nkb; ++kb) {
                                 mbar_wait(smem_u32(&bars->wfull[s]), ph);
                                 tc_fence_after();
@@ -238,8 +281,11 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                                 umma_commit(smem_u32(&bars->wempty[s]));
                                 if (++s == kWStages) { s = 0; ph ^= 1u; }
                             }
+                            // the epilogue overwrites the operand buffer once it sees this commit: the stores must have read it
+                            if constexpr (kTrain) tma_store_wait_read();
                             umma_commit(smem_u32(&bars->accfull[sub]));
                         }
+                if constexpr (kTrain) tma_store_wait_all();
             }
             __syncwarp();
         }
@@ -313,13 +359,17 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
 #pragma unroll
             for (int sub = 0; sub < 2; ++sub) load_x(next < num_tiles ? next * kTileRows + sub * 128 + r : M, xn[sub]);
 #pragma unroll 1
-            for (int l = 0; l < L; ++l) {
-                const bool last = l == L - 1;
+            for (int l = 0; l < LT; ++l) {
+                const bool last = l == L - 1;                 // last hidden layer: its output also feeds the sdf head
+                const bool head = kTrain && l == L;           // feature head (training only): linear, rows leave for the colour net
                 const bool skip = l == P.skip_after;
+                const bool writes_act = kTrain ? !head : !last;
+                const float os = kTrain ? P.oscale[l < L ? l : 0] : 1.0f;
 #pragma unroll
                 for (int sub = 0; sub < 2; ++sub) {
                     const uint32_t act = sAct + (uint32_t)sub * kActBytes;
                     const uint32_t tacc = tmem_base + tlane + (uint32_t)sub * 256u;
+                    const int64_t grow = tile * kTileRows + sub * 128 + r;
                     mbar_wait(smem_u32(&bars->accfull[sub]), sub == 0 ? par0 : par1);
                     if (sub == 0) par0 ^= 1u; else par1 ^= 1u;
                     tc_fence_after();
@@ -331,7 +381,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                         // the next layer's bias for this chunk is fetched BEFORE the math so that its store never waits
                         uint32_t acc[32], bb[32];
                         tmem_ld32_issue(tacc + (uint32_t)c * 32u, acc);
-                        if (!last) {
+                        if (writes_act) {
                             const float4* src = reinterpret_cast<const float4*>(P.bias + (l + 1) * 256 + c * 32);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -341,65 +391,97 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                             }
                         }
                         tmem_ld32_wait(acc);
-                        if (!last) {
-                            if (skip && i == 1) {                            // the skip concat's columns live in chunks 5 .. 7
-                                float h[32];
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) h[j] = softplus_scaled(__uint_as_float(acc[j]));
-                                float hf[kNf > 0 ? kNf : 1];
-                                load_hf<kNf>(hashf, tile * kTileRows + sub * 128 + r, M, hf);
-                                if (g == 1) skip_fix<kPeW, kD0, 5>(xc[sub], hf, h);
-                                else if (g == 2) skip_fix<kPeW, kD0, 6>(xc[sub], hf, h);
-                                else if (g == 3) skip_fix<kPeW, kD0, 7>(xc[sub], hf, h);
-                                uint32_t w[16];
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) w[j] = pack_h2(h[2 * j], h[2 * j + 1]);
-                                store_chunk(act, r, c, w);
-                            } else {
-                                // 8 columns at a time: activation, pack, one 16-byte store into the swizzled operand row
-                                const uint32_t cbase = act + (uint32_t)(c >> 1) * kKBlockBytes + rowoff + ((uint32_t)((c & 1) << 6) ^ swhi);
+                        if (head) {
+                            // feature head: acc + bias (preset) -> fp16 -> the colour net's input row, 64 contiguous bytes per lane
+                            if (P.feat != nullptr && grow < M) {
+                                uint4* dst = reinterpret_cast<uint4*>(P.feat + grow * P.ldfeat + c * 32);
 #pragma unroll
                                 for (int p = 0; p < 4; ++p) {
-                                    uint32_t w[4];
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j)
-                                        w[j] = pack_h2(softplus_scaled(__uint_as_float(acc[8 * p + 2 * j])),
-                                                       softplus_scaled(__uint_as_float(acc[8 * p + 2 * j + 1])));
-                                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + swlo[p]), "r"(w[0]), "r"(w[1]),
-                                                 "r"(w[2]), "r"(w[3]) : "memory");
+                                    uint4 q;
+                                    q.x = pack_h2(__uint_as_float(acc[8 * p]), __uint_as_float(acc[8 * p + 1]));
+                                    q.y = pack_h2(__uint_as_float(acc[8 * p + 2]), __uint_as_float(acc[8 * p + 3]));
+                                    q.z = pack_h2(__uint_as_float(acc[8 * p + 4]), __uint_as_float(acc[8 * p + 5]));
+                                    q.w = pack_h2(__uint_as_float(acc[8 * p + 6]), __uint_as_float(acc[8 * p + 7]));
+                                    dst[p] = q;
                                 }
                             }
-                            tmem_st32(tacc + (uint32_t)c * 32u, bb);
-                        } else {
+                            continue;
+                        }
+                        if (last) {                                         // sdf head: dot with the fp32 activations
                             const float4* wl4 = reinterpret_cast<const float4*>(P.w_last + c * 32);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float4 t4 = __ldg(wl4 + j);
-                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j])), t4.x, dot);
-                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 1])), t4.y, dot);
-                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 2])), t4.z, dot);
-                                dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 3])), t4.w, dot);
+                                if constexpr (kTrain) {
+                                    // (keep the activations: they are stored below)
+                                    float h0 = softplus_plain(__uint_as_float(acc[4 * j])), h1 = softplus_plain(__uint_as_float(acc[4 * j + 1]));
+                                    float h2 = softplus_plain(__uint_as_float(acc[4 * j + 2])), h3 = softplus_plain(__uint_as_float(acc[4 * j + 3]));
+                                    dot = fmaf(h0, t4.x, dot); dot = fmaf(h1, t4.y, dot); dot = fmaf(h2, t4.z, dot); dot = fmaf(h3, t4.w, dot);
+                                    acc[4 * j] = __float_as_uint(h0); acc[4 * j + 1] = __float_as_uint(h1);
+                                    acc[4 * j + 2] = __float_as_uint(h2); acc[4 * j + 3] = __float_as_uint(h3);
+                                } else {
+                                    dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j])), t4.x, dot);
+                                    dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 1])), t4.y, dot);
+                                    dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 2])), t4.z, dot);
+                                    dot = fmaf(softplus_scaled(__uint_as_float(acc[4 * j + 3])), t4.w, dot);
+                                }
+                            }
+                            if constexpr (!kTrain) continue;
+                        }
+                        // hidden layer (and, when training, the last one: its activations are already in acc)
+                        if (skip && i == 1) {                            // the skip concat's columns live in chunks 5 .. 7
+                            float h[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) h[j] = kTrain ? softplus_plain(__uint_as_float(acc[j])) : softplus_scaled(__uint_as_float(acc[j]));
+                            float hf[kNf > 0 ? kNf : 1];
+                            load_hf<kNf>(hashf, grow, M, hf);
+                            if (g == 1) skip_fix<kPeW, kD0, 5>(xc[sub], hf, h);
+                            else if (g == 2) skip_fix<kPeW, kD0, 6>(xc[sub], hf, h);
+                            else if (g == 3) skip_fix<kPeW, kD0, 7>(xc[sub], hf, h);
+                            uint32_t w[16];
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) w[j] = pack_h2(h[2 * j] * os, h[2 * j + 1] * os);
+                            store_chunk(act, r, c, w);
+                        } else {
+                            // 8 columns at a time: activation, pack, one 16-byte store into the swizzled operand row
+                            const uint32_t cbase = act + (uint32_t)(c >> 1) * kKBlockBytes + rowoff + ((uint32_t)((c & 1) << 6) ^ swhi);
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) {
+                                uint32_t w[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float h0 = __uint_as_float(acc[8 * p + 2 * j]), h1 = __uint_as_float(acc[8 * p + 2 * j + 1]);
+                                    if constexpr (kTrain) {
+                                        if (!last) { h0 = softplus_plain(h0); h1 = softplus_plain(h1); }
+                                        h0 *= os; h1 *= os;
+                                    } else {
+                                        h0 = softplus_scaled(h0); h1 = softplus_scaled(h1);
+                                    }
+                                    w[j] = pack_h2(h0, h1);
+                                }
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cbase + swlo[p]), "r"(w[0]), "r"(w[1]),
+                                             "r"(w[2]), "r"(w[3]) : "memory");
                             }
                         }
+                        tmem_st32(tacc + (uint32_t)c * 32u, bb);
                     }
-                    if (!last) {
+                    if (writes_act) {
                         tmem_st_wait();
                         fence_proxy_async();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&bars->actready[sub]));
-                    } else {
-                        // sdf = dot over all 256 columns: the four warps of the quadrant combine through the tail of the
-                        // sub-tile's operand buffer (free until the next layer-0 epilogue rewrites it)
-                        const uint32_t slot = act + 3u * kKBlockBytes + (uint32_t)(g * 128 + r) * 4u;
-                        if (g != 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(dot) : "memory");
+                    }
+                    if (last) {
+                        // sdf = dot over all 256 columns: the four warps of a quadrant combine through three 512-byte slots
+                        // behind the barriers (fixed order: deterministic); the second barrier lets the slots be reused
+                        if (g != 0) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sPart + (uint32_t)((g - 1) * 128 + r) * 4u), "f"(dot) : "memory");
                         named_bar_sync(1 + q, 128);
                         if (g == 0) {
                             float o1, o2, o3;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o1) : "r"(slot + 512u) : "memory");
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o2) : "r"(slot + 1024u) : "memory");
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o3) : "r"(slot + 1536u) : "memory");
-                            const int64_t grow = tile * kTileRows + sub * 128 + r;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o1) : "r"(sPart + (uint32_t)r * 4u) : "memory");
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o2) : "r"(sPart + (uint32_t)(128 + r) * 4u) : "memory");
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o3) : "r"(sPart + (uint32_t)(256 + r) * 4u) : "memory");
                             float sdf = ((dot + o1) + (o2 + o3)) + __ldg(P.b_last);
                             if (P.clamp_radius > 0.f) {
                                 const float* p3 = xc[sub];
@@ -407,6 +489,9 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                             }
                             if (grow < M) sdf_out[grow] = sdf;
                         }
+                        named_bar_sync(1 + q, 128);
+                    }
+                    if (l == LT - 1) {
                         // this sub-tile's accumulator and operand buffer are free: the next tile's input goes in
                         xc[sub][0] = xn[sub][0]; xc[sub][1] = xn[sub][1]; xc[sub][2] = xn[sub][2];
                         if (next < num_tiles) produce_input(sub, xc[sub], next * kTileRows + sub * 128 + r);
@@ -421,37 +506,52 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-// Packed parameters of the scaled domain (c = kScale):
+// Packed parameters.  Scaled domain (sdf-only queries, c = kScale):
 //   Wp[(l * 256 + r) * 256 + k] = fp16(W_l[r, k] * s_l(k)), zero padded; s = c for layer 0 (unscaled input), 1 otherwise;
 //        the skip layer: 1/sqrt2 on the columns of the previous layer's (scaled) output, c/sqrt2 on the input's columns
 //   bp[l * 256 + r] = c b_l[r];   wl[k] = W_last[0, k] / c
+// Plain domain (training forward): the weights as they are (the stored activations carry the 1/sqrt2 of the skip concat),
+//   plus one more layer: rows 1 .. 256 of the last linear layer (the feature head) with their biases.
 struct PackArgs {
     int L;
     const float* W[kMaxL]; const float* b[kMaxL];
     int out[kMaxL], in[kMaxL]; int64_t ldw[kMaxL];
     int skip, skip_col;                 // skip layer (-1: none) and its first input column
-    const float* w_last; int in_last;
+    const float* w_last; const float* b_last; int in_last; int64_t ldw_last;
+    int plain, feat_rows;               // plain domain; rows of the feature head (0: none)
 };
 __global__ void k_pack_fused(const __grid_constant__ PackArgs a, __half* __restrict__ Wp, float* __restrict__ bp, float* __restrict__ wl) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nW = (int64_t)a.L * 65536;
+    const int LT = a.L + (a.feat_rows > 0 ? 1 : 0);
+    const int64_t nW = (int64_t)LT * 65536;
     if (i < nW) {
         const int l = (int)(i >> 16), r = (int)((i >> 8) & 255), k = (int)(i & 255);
-        float sc = l == 0 ? kScale : 1.0f;
-        if (l == a.skip) sc = (k < a.skip_col ? 1.0f : kScale) * 0.70710678118654752440f;
-        const float v = (r < a.out[l] && k < a.in[l]) ? a.W[l][(int64_t)r * a.ldw[l] + k] * sc : 0.f;
+        float v = 0.f;
+        if (l == a.L) {                 // feature head: rows 1 .. of the last layer
+            if (r < a.feat_rows && k < a.in_last) v = a.w_last[(int64_t)(r + 1) * a.ldw_last + k];
+        } else {
+            float sc = 1.0f;
+            if (!a.plain) {
+                sc = l == 0 ? kScale : 1.0f;
+                if (l == a.skip) sc = (k < a.skip_col ? 1.0f : kScale) * 0.70710678118654752440f;
+            }
+            if (r < a.out[l] && k < a.in[l]) v = a.W[l][(int64_t)r * a.ldw[l] + k] * sc;
+        }
         Wp[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-    } else if (i < nW + (int64_t)a.L * 256) {
+    } else if (i < nW + (int64_t)LT * 256) {
         const int64_t t = i - nW;
         const int l = (int)(t >> 8), r = (int)(t & 255);
-        bp[t] = r < a.out[l] ? a.b[l][r] * kScale : 0.f;
-    } else if (i < nW + (int64_t)a.L * 256 + 256) {
-        const int k = (int)(i - nW - (int64_t)a.L * 256);
-        wl[k] = k < a.in_last ? a.w_last[k] / kScale : 0.f;
+        float v = 0.f;
+        if (l == a.L) { if (r < a.feat_rows) v = a.b_last[r + 1]; }
+        else if (r < a.out[l]) v = a.b[l][r] * (a.plain ? 1.0f : kScale);
+        bp[t] = v;
+    } else if (i < nW + (int64_t)LT * 256 + 256) {
+        const int k = (int)(i - nW - (int64_t)LT * 256);
+        wl[k] = k < a.in_last ? a.w_last[k] * (a.plain ? 1.0f : 1.0f / kScale) : 0.f;
     }
 }
 
-inline size_t fused_workspace_bytes(int L) { return (size_t)L * 131072 + (size_t)L * 1024 + 1024; }
+inline size_t fused_workspace_bytes(int L) { return (size_t)(L + 1) * 131072 + (size_t)(L + 1) * 1024 + 1024; }   // (+ the feature head)
 
 // can the network run fused?  hidden widths 256 (the layer before the skip: 256 - d0), at most 128 encoded inputs
 inline bool fused_supported(int nl, const int* in, const int* out, int skip, int d0, int pe_w) {

@@ -1184,6 +1184,7 @@ struct Bufs {
     float *G0, *G0b, *BH0, *dydx, *hashf, *sdf_raw, *mask, *dn, *dn_color, *gradc, *sdfc, *dcode;   // G0b: the skip layer's share of d sdf / d h0
     float *spec32, *dspec32;   // spec variant: specular head output / its adjoint, [Mc, 3]
     TF* X; TF* C[MSDF_MAX_LAYERS]; T* dC[2]; T* Hd;   // Hd: colour head dpre, [Mc, 64] (bf16 mode)
+    char* fusedW;              // packed parameters of the fused forward kernel (tensor-core mode)
     T* adj(int l) const { return reinterpret_cast<T*>(A[l]); }   // A[l] once it holds z_l / pbar_l
     int64_t d0p, ldh, ldo, ldx, ldc;   // leading dimensions
 };
@@ -1231,6 +1232,8 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
                 if (dst[k]) { dst[k]->Wk[l] = wk; dst[k]->Wt[l] = wt; dst[k]->Wkb[l] = wkb; dst[k]->Wtb[l] = wtb; }
             }
     }
+    if (kIsBf16<T> && mode != MSDF_MODE_SDF_ONLY)
+        b.fusedW = c.take<char>(1, (int64_t)msdf_fused::fused_workspace_bytes(sn.L - 1));
     const bool grid_feats = enc->grid_feat_dim > 0 && enc->table != nullptr;
     b.d0p = padw<T>(sn.d0); b.ldh = padw<T>(sn.maxw);
     b.H[0] = p.take<TF>(Mc, b.d0p);
@@ -1751,66 +1754,118 @@ bool fused_applicable(const Ctx& c) {
     return g_fused_enabled && msdf_fused::fused_supported(c.sn.L, c.sn.in, c.sn.out, c.sn.skip, c.sn.d0, c.pe_w);
 }
 
-int fused_sdf_only(const Ctx& c, const float* x, int64_t M, void* workspace, size_t workspace_bytes, float* sdf, const char* who) {
+// packed parameters + weight tensor map + plan of one fused launch series (scaled domain: sdf-only; plain: training forward)
+struct FusedPrep { msdf_fused::Plan P; CUtensorMap mW; };
+
+int fused_prepare(const Ctx& c, char* ws, bool train, FusedPrep& fp, const char* who) {
+    namespace mf = msdf_fused;
+    const Net& n = c.sn;
+    const int L = n.L - 1, LT = L + (train ? 1 : 0);
+    __half* Wp = reinterpret_cast<__half*>(ws);
+    float* bp = reinterpret_cast<float*>(ws + (size_t)LT * 131072);
+    float* wl = bp + (size_t)LT * 256;
+    mf::PackArgs pa{};
+    mf::Plan& P = fp.P;
+    P = mf::Plan{};
+    pa.L = L; P.L = L;
+    for (int l = 0; l < L; ++l) {
+        pa.W[l] = n.W[l]; pa.b[l] = n.b[l]; pa.out[l] = n.out[l]; pa.in[l] = n.in[l]; pa.ldw[l] = n.ldw[l];
+        P.kb[l] = round_up(n.in[l], 64) / 64;
+        P.oscale[l] = l + 1 == n.skip ? kInvSqrt2 : 1.0f;
+    }
+    P.kb[L] = 4;
+    pa.w_last = n.W[L]; pa.b_last = n.b[L]; pa.in_last = n.in[L]; pa.ldw_last = n.ldw[L];
+    pa.skip = n.skip > 0 ? n.skip : -1; pa.skip_col = n.skip > 0 ? n.out[n.skip - 1] : 0;
+    pa.plain = train ? 1 : 0; pa.feat_rows = train ? n.out[L] - 1 : 0;
+    P.skip_after = n.skip > 0 ? n.skip - 1 : -1;
+    P.bias = bp; P.w_last = wl; P.b_last = n.b[L];
+    P.clamp_radius = train ? 0.f : c.clamp_radius; P.sphere_scale = c.sphere_scale;
+    const int64_t total = (int64_t)LT * 65536 + (int64_t)LT * 256 + 256;
+    mf::k_pack_fused<<<nblk(total), 256, 0, c.st>>>(pa, Wp, bp, wl);
+    LAUNCHED("fused weight pack");
+    return msdf_tc::make_map(&fp.mW, Wp, msdf_tc::kF16, (int64_t)LT * 256, 256, 256, 256, who);
+}
+
+// one launch over Mc points.  train: maps of the saved inputs H[0 .. L] and the feature rows (may be null)
+int fused_launch(const Ctx& c, const FusedPrep& fp, bool train, const float* x, const float* hashf, int64_t Mc, float* sdf,
+                 const msdf_fused::StoreMaps* sm, __half* feat, int64_t ldfeat, const char* who) {
     namespace mf = msdf_fused;
     const Net& n = c.sn;
     const int L = n.L - 1;
+    const int variant = (n.d0 == 39 ? 0 : 1) + (train ? 2 : 0);
+    using Kern = void (*)(const CUtensorMap, const mf::Plan, const mf::StoreMaps, const float*, const float*, int64_t, float*);
+    static const Kern kerns[4] = {mf::k_fused_sdf<39, 39, false>, mf::k_fused_sdf<39, 71, false>, mf::k_fused_sdf<39, 39, true>,
+                                  mf::k_fused_sdf<39, 71, true>};
+    static bool attr_set[4] = {false, false, false, false};
+    if (!attr_set[variant]) {
+        cudaError_t e = cudaFuncSetAttribute(kerns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { msdf_set_error("%s: cannot opt in to 227 KB shared memory: %s", who, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
+        attr_set[variant] = true;
+    }
+    const size_t smem = 1024 + 2 * mf::kActBytes + mf::kWStages * mf::kWStageBytes + mf::kFusedTailBytes;
+    mf::Plan P = fp.P;
+    P.feat = feat; P.ldfeat = ldfeat;
+    static const mf::StoreMaps no_maps{};
+    double kcols = train ? 256.0 : 0.0;
+    for (int l = 0; l < L; ++l) kcols += 64.0 * P.kb[l];
+    const int64_t tiles = (Mc + mf::kTileRows - 1) / mf::kTileRows;
+    const int grid = (int)(tiles < msdf_tc::sm_count() ? tiles : msdf_tc::sm_count());
+    const int gw = c.grid ? c.enc->grid_feat_dim : 0;
+    const double bytes = train ? (double)Mc * (16.0 + 4.0 * gw + 2.0 * (round_up(n.d0, 64) + 256.0 * L + (feat ? 256.0 : 0.0)))
+                               : (double)Mc * (16.0 + 4.0 * gw);
+    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)Mc * 256.0 * kcols, c.st, bytes);
+    kerns[variant]<<<grid, mf::kFusedThreads, smem, c.st>>>(fp.mW, P, sm ? *sm : no_maps, x, hashf, Mc, sdf);
+    msdf_prof_end(prof, c.st);
+    LAUNCHED("fused sdf network");
+    return MSDF_OK;
+}
+
+int fused_sdf_only(const Ctx& c, const float* x, int64_t M, void* workspace, size_t workspace_bytes, float* sdf, const char* who) {
+    namespace mf = msdf_fused;
+    const int L = c.sn.L - 1;
     const size_t fixed = mf::fused_workspace_bytes(L);
     const int gw = c.grid ? c.enc->grid_feat_dim : 0;
     MSDF_CHECK_ARG(sdf != nullptr, "%s: sdf output missing", who);
     MSDF_CHECK_ARG(workspace_bytes >= fixed + (size_t)gw * 4 * 256, "%s: workspace of %zu bytes is too small for the fused sdf kernel (%zu)",
                    who, workspace_bytes, fixed + (size_t)gw * 4 * 256);
     char* ws = (char*)workspace;
-    __half* Wp = reinterpret_cast<__half*>(ws);
-    float* bp = reinterpret_cast<float*>(ws + (size_t)L * 131072);
-    float* wl = bp + (size_t)L * 256;
     float* hashf = gw > 0 ? reinterpret_cast<float*>(ws + fixed) : nullptr;
     int64_t chunk = M;
     if (gw > 0) {
         const int64_t cap = (int64_t)((workspace_bytes - fixed) / ((size_t)gw * 4)) / 256 * 256;
         if (chunk > cap) chunk = cap;
     }
-    mf::PackArgs pa{};
-    mf::Plan P{};
-    pa.L = L; P.L = L;
-    for (int l = 0; l < L; ++l) {
-        pa.W[l] = n.W[l]; pa.b[l] = n.b[l]; pa.out[l] = n.out[l]; pa.in[l] = n.in[l]; pa.ldw[l] = n.ldw[l];
-        P.kb[l] = round_up(n.in[l], 64) / 64;
-    }
-    pa.w_last = n.W[L]; pa.in_last = n.in[L];
-    pa.skip = n.skip > 0 ? n.skip : -1; pa.skip_col = n.skip > 0 ? n.out[n.skip - 1] : 0;
-    P.skip_after = n.skip > 0 ? n.skip - 1 : -1;
-    P.bias = bp; P.w_last = wl;
-    P.clamp_radius = c.clamp_radius; P.sphere_scale = c.sphere_scale;
-    const int64_t total = (int64_t)L * 65536 + (int64_t)L * 256 + 256;
-    mf::k_pack_fused<<<nblk(total), 256, 0, c.st>>>(pa, Wp, bp, wl);
-    LAUNCHED("fused weight pack");
-    P.b_last = n.b[L];
-    CUtensorMap mW;
-    RUN(msdf_tc::make_map(&mW, Wp, msdf_tc::kF16, (int64_t)L * 256, 256, 256, 256, who));
-    auto kern = n.d0 == 39 ? mf::k_fused_sdf<39, 39> : mf::k_fused_sdf<39, 71>;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[n.d0 == 39]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) { msdf_set_error("%s: cannot opt in to 227 KB shared memory: %s", who, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
-        attr_set[n.d0 == 39] = true;
-    }
-    const size_t smem = 1024 + 2 * mf::kActBytes + mf::kWStages * mf::kWStageBytes + sizeof(mf::FusedBarriers);
-    double kcols = 0.0;
-    for (int l = 0; l < L; ++l) kcols += 64.0 * P.kb[l];
+    FusedPrep fp;
+    RUN(fused_prepare(c, ws, false, fp, who));
     for (int64_t m0 = 0; m0 < M; m0 += chunk) {
         const int64_t Mc = M - m0 < chunk ? M - m0 : chunk;
         if (gw > 0)
             RUN(msdf_hash_forward_rows(x + 3 * m0, c.enc->table, c.enc->offsets, hashf, gw, Mc, c.enc->level_dim, c.enc->n_levels,
                                        c.enc->log2_per_level_scale, (uint32_t)c.enc->base_res, c.enc->divide_factor, nullptr, c.st));
-        const int64_t tiles = (Mc + mf::kTileRows - 1) / mf::kTileRows;
-        const int grid = (int)(tiles < msdf_tc::sm_count() ? tiles : msdf_tc::sm_count());
-        const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)Mc * 256.0 * kcols, c.st, (double)Mc * (16.0 + 4.0 * gw));
-        kern<<<grid, mf::kFusedThreads, smem, c.st>>>(mW, P, x + 3 * m0, hashf, Mc, sdf + m0);
-        msdf_prof_end(prof, c.st);
-        LAUNCHED("fused sdf network");
+        RUN(fused_launch(c, fp, false, x + 3 * m0, hashf, Mc, sdf + m0, nullptr, nullptr, 0, who));
     }
     return MSDF_OK;
+}
+
+// training / rendering forward of one chunk: hash features (+ dy_dx), then ONE launch that leaves H[0 .. L], the raw sdf and
+// the feature rows (replaces encode + the per-layer forward sweep + sdf head + feature head)
+bool fused_train_applicable(const Ctx& c) {
+    return fused_applicable(c) && c.sn.out[c.sn.L - 1] == 257;
+}
+template <class T>
+int fused_forward_chunk(const Ctx& c, const Bufs<T>& b, const FusedPrep& fp, const float* x, int64_t Mc, Fw<T>* feat, int64_t ldf_,
+                        bool want_dydx, const char* who) {
+    namespace mf = msdf_fused;
+    const Net& n = c.sn;
+    const int L = n.L - 1;
+    if (c.grid)
+        RUN(msdf_hash_forward_rows(x, c.enc->table, c.enc->offsets, b.hashf, c.enc->grid_feat_dim, Mc, c.enc->level_dim, c.enc->n_levels,
+                                   c.enc->log2_per_level_scale, (uint32_t)c.enc->base_res, c.enc->divide_factor,
+                                   want_dydx ? b.dydx : nullptr, c.st));
+    mf::StoreMaps sm{};
+    for (int l = 0; l <= L; ++l)
+        RUN(msdf_tc::make_map(&sm.m[l], b.H[l], msdf_tc::kF16, Mc, l == 0 ? b.d0p : 256, l == 0 ? b.d0p : b.ldh, 128, who));
+    return fused_launch(c, fp, true, x, c.grid ? b.hashf : nullptr, Mc, b.sdf_raw, &sm, reinterpret_cast<__half*>(feat), ldf_, who);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -1851,16 +1906,27 @@ int field_forward(Ctx& c, const float* x, int64_t M, const float* view_dirs, int
     }
     const bool with_grad = mode == MSDF_MODE_FORWARD && (grad != nullptr);
     MSDF_CHECK_ARG(!(kIsBf16<T> && feat != nullptr), "%s: the raw feature output is only available in fp32 mode", who);
+    // tensor-core mode: the forward sweep of every chunk is ONE launch of the fused kernel (fused_mlp.cuh, kTrain)
+    bool fused_fwd = false;
+    FusedPrep fprep;
+    if constexpr (kIsBf16<T>) {
+        fused_fwd = mode == MSDF_MODE_FORWARD && fused_train_applicable(c) && b.fusedW != nullptr && b.ldh == 256;
+        if (fused_fwd) RUN(fused_prepare(c, b.fusedW, true, fprep, who));
+    }
     for (int64_t m0 = 0; m0 < M; m0 += chunk) {
         const int64_t Mc = (M - m0 < chunk) ? M - m0 : chunk;
         const float* xc = x + 3 * m0;
         if (saving && m0 > 0)   // this chunk's slice of the saved buffer (the workspace part is reused)
             carve<T>(c, (chunk + 127) / 128 * 128, mode, workspace, &b, nullptr, nullptr, (char*)saved + stride * (size_t)(m0 / chunk), true);
-        RUN(encode_chunk<T>(c, b, xc, Mc, with_grad));
         Fw<T>* featc = nullptr; int64_t ldf_ = 0;
         if (c.has_color) { featc = b.X + (kIsBf16<T> ? 0 : c.cg.fc); ldf_ = b.ldx; }
         else if (feat != nullptr) { featc = reinterpret_cast<Fw<T>*>(feat + m0 * ld_feat); ldf_ = ld_feat; }
-        RUN(forward_sweep<T>(c, b, Mc, featc, ldf_));
+        if (fused_fwd) {
+            if constexpr (kIsBf16<T>) RUN(fused_forward_chunk<T>(c, b, fprep, xc, Mc, featc, ldf_, with_grad, who));
+        } else {
+            RUN(encode_chunk<T>(c, b, xc, Mc, with_grad));
+            RUN(forward_sweep<T>(c, b, Mc, featc, ldf_));
+        }
         if (with_grad) RUN(reverse_sweep<T>(c, b, Mc));
         RUN(decode_chunk<T>(c, b, xc, Mc, with_grad, sdf ? sdf + m0 : nullptr, with_grad ? grad + 3 * m0 : nullptr,
                             saving ? b.mask : nullptr));
@@ -1905,6 +1971,12 @@ int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, in
         RUN(prep_weights(c, c.sn, 1));
         if (c.has_color) { c.cn.rot0 = c.cg.fc; RUN(prep_weights(c, c.cn, 0)); }
     }
+    bool fused_fwd = false;
+    FusedPrep fprep;
+    if constexpr (kIsBf16<T>) {
+        fused_fwd = !have_saved && fused_train_applicable(c) && b.fusedW != nullptr && b.ldh == 256;
+        if (fused_fwd) RUN(fused_prepare(c, b.fusedW, true, fprep, who));
+    }
     const int out_last = c.sn.out[c.sn.L - 1];
     const int feat_w = out_last - 1;
     const int sdf_col = kIsBf16<T> ? feat_w : 0, feat_col0 = kIsBf16<T> ? 0 : 1;
@@ -1918,8 +1990,13 @@ int field_backward(Ctx& c, const float* x, int64_t M, const float* view_dirs, in
                          (char*)saved + stride * (size_t)(m0 / chunk), true);
         } else {
             // ---- recompute the chunk
-            RUN(encode_chunk<T>(c, b, xc, Mc, true));
-            RUN(forward_sweep<T>(c, b, Mc, c.has_color ? b.X + (kIsBf16<T> ? 0 : c.cg.fc) : nullptr, c.has_color ? b.ldx : 0));
+            if (fused_fwd) {
+                if constexpr (kIsBf16<T>)
+                    RUN(fused_forward_chunk<T>(c, b, fprep, xc, Mc, c.has_color ? b.X : nullptr, c.has_color ? b.ldx : 0, true, who));
+            } else {
+                RUN(encode_chunk<T>(c, b, xc, Mc, true));
+                RUN(forward_sweep<T>(c, b, Mc, c.has_color ? b.X + (kIsBf16<T> ? 0 : c.cg.fc) : nullptr, c.has_color ? b.ldx : 0));
+            }
             RUN(reverse_sweep<T>(c, b, Mc));
             RUN(decode_chunk<T>(c, b, xc, Mc, true, b.sdfc, b.gradc, b.mask));
         }
