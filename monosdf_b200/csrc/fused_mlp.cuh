@@ -61,7 +61,7 @@ struct StoreMaps { CUtensorMap m[kMaxL + 1]; };     // kTrain: H[l], the saved i
 
 
 struct FusedBarriers {
-    uint64_t wfull[kWStages], wempty[kWStages], actready[2], accfull[2];
+    uint64_t wfull[kWStages], wempty[kWStages], actready[2], accfull[2], storedone[2];
     uint32_t tmem_base, pad;
 };
 static_assert(sizeof(FusedBarriers) <= 128, "the partial-sum slots start 128 bytes behind the barriers");
@@ -118,6 +118,28 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// EXPERIMENT (off): the scaled softplus on packed fp16 pairs -- HMNMX2 + three HFMA2 per pair, 4 issue slots per activation
+// instead of 6.5.  Measured: no faster (8.45 vs 8.25 ms for 8.4 M points) and less accurate (one more fp16 rounding per
+// layer): ex2.approx.f16x2 is TWO MUFU.EX2.F16 + a PRMT, so the XU pipe -- 32768 results per 2048-clock MMA pass at
+// 16 / clk / SM, i.e. exactly the MMA time -- stays the limiter, not the issue slots.
+#ifndef MSDF_FUSED_HALF2
+#define MSDF_FUSED_HALF2 0
+#endif
+__device__ __forceinline__ uint32_t softplus_scaled_h2(float lo, float hi) {
+    const uint32_t vp = WarpIO::pack2<kF16>(lo, hi);                       // cvt.rn.satfinite.f16x2.f32
+    const __half2 v = *reinterpret_cast<const __half2*>(&vp);
+    // (h2exp2() goes through fp32; the PTX instruction maps to two MUFU.EX2.F16, one per half, no conversions)
+    const __half2 na = __hneg2(__habs2(v));
+    uint32_t tp;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(tp) : "r"(*reinterpret_cast<const uint32_t*>(&na)));
+    const __half2 t = *reinterpret_cast<const __half2*>(&tp);
+    const __half2 c1 = __float2half2_rn(kC1), c2 = __float2half2_rn(kC2), c3 = __float2half2_rn(kC3);
+    __half2 p = __hfma2(c3, t, c2);
+    p = __hfma2(p, t, c1);
+    const __half2 h = __hfma2(p, t, __hmax2(v, __float2half2_rn(0.f)));
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t r[32]) {
     asm volatile(
@@ -220,7 +242,10 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < kWStages; ++s) { mbar_init(smem_u32(&bars->wfull[s]), 1); mbar_init(smem_u32(&bars->wempty[s]), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->actready[s]), kFusedEpiWarps); mbar_init(smem_u32(&bars->accfull[s]), 1); }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&bars->actready[s]), kFusedEpiWarps); mbar_init(smem_u32(&bars->accfull[s]), 1);
+            mbar_init(smem_u32(&bars->storedone[s]), 1);
+        }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
@@ -263,12 +288,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                             const uint32_t tmem_d = tmem_base + (uint32_t)sub * 256u;
                             const uint32_t act = sAct + (uint32_t)sub * kActBytes;
                             const int nkb = P.kb[l];
-                            if constexpr (kTrain) {
-                                // H[l] <- the operand tile (the epilogue warps fenced their writes for the async proxy)
-                                const int row = (int)(tile * kTileRows + sub * 128);
-                                for (int kb = 0; kb < nkb; ++kb) tma_store_2d(&SM.m[l], act + (uint32_t)kb * kKBlockBytes, kb * BK, row);
-                                tma_store_commit();
-                            }
+
                             for (int kb = 0; kb < nkb; ++kb) {
                                 mbar_wait(smem_u32(&bars->wfull[s]), ph);
                                 tc_fence_after();
@@ -281,13 +301,34 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                                 umma_commit(smem_u32(&bars->wempty[s]));
                                 if (++s == kWStages) { s = 0; ph ^= 1u; }
                             }
-                            // the epilogue overwrites the operand buffer once it sees this commit: the stores must have read it
-                            if constexpr (kTrain) tma_store_wait_read();
                             umma_commit(smem_u32(&bars->accfull[sub]));
                         }
-                if constexpr (kTrain) tma_store_wait_all();
             }
             __syncwarp();
+        } else if (warp == 2) {
+            if constexpr (kTrain) {
+                if (lane == 0) {
+                    // ---- store warp: H[l] <- the operand tile of every (layer, sub-tile) pass, as soon as the epilogue has
+                    // written it (its writes are fenced for the async proxy); storedone tells the epilogue warps that the
+                    // tile has been read and may be overwritten.  (In the MMA warp these waits stalled the tensor pipe.)
+                    uint32_t par0 = 0u, par1 = 0u;
+                    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x)
+                        for (int l = 0; l < LT; ++l)
+#pragma unroll
+                            for (int sub = 0; sub < 2; ++sub) {
+                                mbar_wait(smem_u32(&bars->actready[sub]), sub == 0 ? par0 : par1);
+                                if (sub == 0) par0 ^= 1u; else par1 ^= 1u;
+                                const uint32_t act = sAct + (uint32_t)sub * kActBytes;
+                                const int row = (int)(tile * kTileRows + sub * 128);
+                                for (int kb = 0; kb < P.kb[l]; ++kb) tma_store_2d(&SM.m[l], act + (uint32_t)kb * kKBlockBytes, kb * BK, row);
+                                tma_store_commit();
+                                tma_store_wait_read();
+                                mbar_arrive(smem_u32(&bars->storedone[sub]));
+                            }
+                    tma_store_wait_all();
+                }
+                __syncwarp();
+            }
         }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFusedRegsEpi));
@@ -371,6 +412,7 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                     const uint32_t tacc = tmem_base + tlane + (uint32_t)sub * 256u;
                     const int64_t grow = tile * kTileRows + sub * 128 + r;
                     mbar_wait(smem_u32(&bars->accfull[sub]), sub == 0 ? par0 : par1);
+                    if constexpr (kTrain) mbar_wait(smem_u32(&bars->storedone[sub]), sub == 0 ? par0 : par1);   // same sequence of phases
                     if (sub == 0) par0 ^= 1u; else par1 ^= 1u;
                     tc_fence_after();
                     float dot = 0.f;
@@ -455,7 +497,12 @@ k_fused_sdf(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ Pl
                                         if (!last) { h0 = softplus_plain(h0); h1 = softplus_plain(h1); }
                                         h0 *= os; h1 *= os;
                                     } else {
+#if MSDF_FUSED_HALF2 && MSDF_FUSED_POLY == 3
+                                        w[j] = softplus_scaled_h2(h0, h1);
+                                        continue;
+#else
                                         h0 = softplus_scaled(h0); h1 = softplus_scaled(h1);
+#endif
                                     }
                                     w[j] = pack_h2(h0, h1);
                                 }
