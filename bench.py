@@ -554,7 +554,7 @@ def run_ours(args):
     traffic = None
     tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")     # dram bytes / launch of the same kernels from ncu --set full
     if os.path.exists(tr_path):
-        traffic = json.load(open(tr_path)).get("tcgen05_gemm_dram_bytes_per_launch")
+        traffic = json.load(open(tr_path)).get("dominant_kernel_dram_bytes_per_launch")
     others = {}
     for cls, name, bound in ((2, "hash grid gather/scatter", "hbm"), (3, "sampler round (warp scans)", "issue"),
                              (4, "compositing fwd+bwd", "hbm")):
@@ -584,7 +584,9 @@ def run_ours(args):
                      # achieved = ALGORITHMIC FLOPs of one step (SURVEY 8d per-ray figure at the measured sampler rounds x rays)
                      # / the time one step spends in those kernels (CUDA events per launch, mean of the instrumented steps)
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": traffic, "peak_source": peak_src,
+                     "traffic": traffic, "traffic_note": "ncu dram bytes per launch of the class's largest kernel (k_tc_gemm<EpiTan>, 262144 "
+                                                          "rows; algorithmic 671 MB); per-kernel table: profiles/ncu_traffic.json",
+                     "peak_source": peak_src,
                      "algorithmic_gflop_per_ray": gflop_per_ray(args.config, rounds), "rays_per_step_per_gpu": n,
                      "launches": g_n, "kernel_ms_per_step": g_ms, "instrumented_step_ms": t_prof,
                      "kernel_share_of_step": g_ms / t_prof if t_prof > 0 else None,
