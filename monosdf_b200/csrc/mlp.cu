@@ -25,6 +25,7 @@
 #include "gemm_f32.cuh"
 #include "tc_gemm.cuh"
 #include "fused_mlp.cuh"
+#include "tc_stream.cuh"
 
 int msdf_hash_forward_rows(const float* x, const float* table, const int* offsets, float* out, int64_t out_ld,
                            int64_t B, int C, int L, float S, uint32_t H, float divide_factor, float* dy_dx, cudaStream_t st);
@@ -829,70 +830,66 @@ struct EpiRev : EpiBase<EpiRev<T>> {
         if (!layer0 && n0 < dh && n0 < this->N) io.prefetch(Hin, ldh, n0, q);
     }
 };
-// tangent sweep, layer l: acc = (t_l W_l^T)[m,n], n over the layer's outputs
+// tangent sweep, layer l: acc = (t_l W_l^T)[m,n], n over the layer's outputs:  t_{l+1} = acc * sigma_l * tscale.
+// (z_l = acc a_l 100 (1 - sigma_l) is NOT formed here any more: the backward sweep rebuilds it from t_{l+1}, a_l and the
+// same sigma -- this sweep then reads one operand back and writes one matrix, like the reverse sweep, instead of 2 + 2.)
 template <class T>
 struct EpiTan : EpiBase<EpiTan<T>> {
     using TF = Fw<T>;
     static constexpr int FF = Fmt16<TF>::value, FA = Fmt16<T>::value;
     const TF* Hn; int64_t ldh; float hscale;       // h_{l+1} as stored (input of layer l+1)
-    TF* AZ; int64_t lda;                           // in: a_l (forward format), out: z_l (adjoint format), in place
     T* Tout; int64_t ldt; float tscale;
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
-        float h[W], a[W], t[W], z[W];
+        float h[W], t[W];
         load_row<W>(Hn + m * ldh + n, h, nv);
-        load_row<W>(AZ + m * lda + n, a, nv);
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-            float s, d;
-            sig_dsig_from_h<kIsBf16<T>>(h[j] * hscale, s, d);
-            t[j] = v[j] * s * tscale;
-            z[j] = v[j] * a[j] * d;
-        }
+        for (int j = 0; j < W; ++j) t[j] = v[j] * sig_from_h<kIsBf16<T>>(h[j] * hscale) * tscale;
         store_row<W>(Tout + m * ldt + n, t, nv);
-        store_row<W>(reinterpret_cast<T*>(AZ) + m * lda + n, z, nv);
     }
     __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
-        uint32_t hp[16], ap[16];      // both operands stay packed; z is packed pair by pair (register budget: 168)
-        io.unstage_packed(q, hp);
-        io.unstage_packed(q + 4, ap);
+        float h[32];
+        io.unstage<FF>(q, h);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float s0, d0, s1, d1;
-            sig_dsig_from_h<true>(WarpIO::unpack<FF>(hp, 2 * j) * hscale, s0, d0);
-            sig_dsig_from_h<true>(WarpIO::unpack<FF>(hp, 2 * j + 1) * hscale, s1, d1);
-            const float z0 = v[2 * j] * WarpIO::unpack<FF>(ap, 2 * j) * d0, z1 = v[2 * j + 1] * WarpIO::unpack<FF>(ap, 2 * j + 1) * d1;
-            v[2 * j] = v[2 * j] * s0 * tscale;
-            v[2 * j + 1] = v[2 * j + 1] * s1 * tscale;
-            ap[j] = WarpIO::pack2<FA>(z0, z1);
-        }
+        for (int j = 0; j < 32; ++j) v[j] = v[j] * sig_from_h<true>(h[j] * hscale) * tscale;
         io.store<FA>(Tout, ldt, n0, v, nv);
-        io.store_packed(AZ, lda, n0, ap, nv);
     }
-    static constexpr int kPre = 2;
-    static constexpr int kStores = 2;
+    static constexpr int kPre = 1;
     __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
-        if (n0 < this->N) { io.prefetch(Hn, ldh, n0, q); io.prefetch(AZ, lda, n0, q + 4); }
+        if (n0 < this->N) io.prefetch(Hn, ldh, n0, q);
     }
 };
-// backward sweep, layer l: acc = (pbar_l W_l)[m,n], n over the layer's inputs
+// backward sweep, layer l: acc = (pbar_l W_l)[m,n], n over the layer's inputs:
+//   pbar_{l-1} = acc * qscale * sigma_{l-1} + z_{l-1},   z_{l-1} = (W_{l-1} t_{l-1}) a_{l-1} 100 (1 - sigma_{l-1})
+// with (W_{l-1} t_{l-1}) recovered from the stored tangent t_l = (W_{l-1} t_{l-1}) sigma_{l-1} tscale_l  (a_{l-1} carries a
+// factor sigma_{l-1} itself, so sigma = 0 means z = 0 on both routes).
 template <class T>
 struct EpiBwd : EpiBase<EpiBwd<T>> {
     using TF = Fw<T>;
     static constexpr int FF = Fmt16<TF>::value, FA = Fmt16<T>::value;
-    const TF* Hin; int64_t ldh; float hscale;
-    T* PZ; int64_t ldp;                            // in: z_{l-1}, out: pbar_{l-1}
+    const TF* Hin; int64_t ldh; float hscale;      // h_l as stored (input of layer l): sigma_{l-1}
+    const T* Tin; int64_t ldt; float inv_tscale;    // t_l (adjoint format) and 1 / its storage scale
+    const TF* Ain; int64_t lda;                     // a_{l-1}
+    T* Pout; int64_t ldp;                           // pbar_{l-1}
     float* bh0; int64_t ldb;                       // adjoint of h_0 (hash-grid nets only), may be null
     int dh; float qscale; int layer0, bh0_accum;
+    template <bool FAST>
+    static __device__ __forceinline__ float combine(float acc_q, float h, float t, float a, float inv_ts) {
+        float sg, d;
+        sig_dsig_from_h<FAST>(h, sg, d);
+        const float z = sg > 0.f ? (FAST ? __fdividef(t * inv_ts, sg) : (t * inv_ts) / sg) * a * d : 0.f;
+        return acc_q * sg + z;
+    }
     template <int W> __device__ __forceinline__ void run(int64_t m, int n, const float* v, int nv) const {
         if (!layer0 && n + nv <= dh) {
-            float h[W], z[W];
+            float h[W], t[W], a[W], o[W];
             load_row<W>(Hin + m * ldh + n, h, nv);
-            load_row<W>(PZ + m * ldp + n, z, nv);
+            load_row<W>(Tin + m * ldt + n, t, nv);
+            load_row<W>(Ain + m * lda + n, a, nv);
 #pragma unroll
-            for (int j = 0; j < W; ++j) z[j] = v[j] * qscale * sig_from_h<kIsBf16<T>>(h[j] * hscale) + z[j];
-            store_row<W>(PZ + m * ldp + n, z, nv);
+            for (int j = 0; j < W; ++j) o[j] = combine<kIsBf16<T>>(v[j] * qscale, h[j] * hscale, t[j], a[j], inv_tscale);
+            store_row<W>(Pout + m * ldp + n, o, nv);
             return;
         }
 #pragma unroll
@@ -902,7 +899,7 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
             const float r = v[j] * qscale;
             if (c >= dh) { if (bh0) bh0[m * ldb + (c - dh)] = r; continue; }
             if (layer0) { if (bh0) { float* g = bh0 + m * ldb + c; *g = bh0_accum ? *g + r : r; } }
-            else { T* p = PZ + m * ldp + c; stf(p, r * sig_from_h<kIsBf16<T>>(ldf(Hin + m * ldh + c) * hscale) + ldf(p)); }
+            else stf(Pout + m * ldp + c, combine<kIsBf16<T>>(r, ldf(Hin + m * ldh + c) * hscale, ldf(Tin + m * ldt + c), ldf(Ain + m * lda + c), inv_tscale));
         }
     }
     __device__ __forceinline__ void chunk(const WarpIO& io, int n0, float v[32], const uint4* q) const {
@@ -923,17 +920,105 @@ struct EpiBwd : EpiBase<EpiBwd<T>> {
             io.store_f32(bh0, ldb, n0 - dh, r, nh > 0 ? nh : 0, nv, false);
         }
         if (nh > 0) {
-            uint32_t hp[16], zp[16];
-            io.unstage_packed(q, hp);
-            io.unstage_packed(q + 4, zp);
+            // three read-back operands, walked 8 columns at a time (16 packed words per operand would not fit next to the
+            // prefetch ring): (h, t) give the sigma part and the z coefficient, then a
+            const uint32_t bh = io.stage(q), bt = io.stage(q + 4);
+            float w[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * qscale * sig_from_h<true>(WarpIO::unpack<FF>(hp, j) * hscale) + WarpIO::unpack<FA>(zp, j);
-            io.store<FA>(PZ, ldp, n0, v, nh);
+            for (int p = 0; p < 4; ++p) {
+                uint32_t hw[4], tw[4];
+                io.piece(bh, p, hw);
+                io.piece(bt, p, tw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float sg, d;
+                    sig_dsig_from_h<true>(WarpIO::unpack<FF>(hw, j) * hscale, sg, d);
+                    w[8 * p + j] = sg > 0.f ? __fdividef(WarpIO::unpack<FA>(tw, j) * inv_tscale, sg) * d : 0.f;
+                    v[8 * p + j] = v[8 * p + j] * qscale * sg;
+                }
+            }
+            __syncwarp();                                  // every lane is done with h before a is staged over it
+            const uint32_t ba = io.stage(q + 8);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                uint32_t aw[4];
+                io.piece(ba, p, aw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[8 * p + j] = fmaf(w[8 * p + j], WarpIO::unpack<FF>(aw, j), v[8 * p + j]);
+            }
+            io.store<FA>(Pout, ldp, n0, v, nh);
         }
     }
-    static constexpr int kPre = 2;
+    static constexpr int kPre = 3;
     __device__ __forceinline__ void prefetch(const WarpIO& io, int n0, uint4* q) const {
-        if (!layer0 && n0 < dh && n0 < this->N) { io.prefetch(Hin, ldh, n0, q); io.prefetch(PZ, ldp, n0, q + 4); }
+        if (!layer0 && n0 < dh && n0 < this->N) { io.prefetch(Hin, ldh, n0, q); io.prefetch(Tin, ldt, n0, q + 4); io.prefetch(Ain, lda, n0, q + 8); }
+    }
+};
+// ---- the same three epilogues for k_tc_stream (tc_stream.cuh): read-back operands arrive as TMA boxes, a thread reads
+// its own row of them 8 columns at a time.  Regular layers only (no h_0 columns, not layer 0): the callers fall back to
+// the k_tc_gemm forms above for the skip layer and layer 0.  Tensor-core mode only.
+template <class T>
+struct EpiTanS : EpiBase<EpiTanS<T>> {            // operand 0: h_{l+1}
+    using TF = Fw<T>;
+    static constexpr int FF = Fmt16<TF>::value, FA = Fmt16<T>::value;
+    static constexpr int kOps = 1;
+    float hscale; T* Tout; int64_t ldt; float tscale;
+    template <int W> __device__ __forceinline__ void run(int64_t, int, const float*, int) const {}
+    __device__ __forceinline__ void chunk_smem(const WarpIO& io, int n0, float v[32], const msdf_tc::OpRow& r) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            uint32_t hw[4];
+            r.piece(0, p, hw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * p + j] = v[8 * p + j] * sig_from_h<true>(WarpIO::unpack<FF>(hw, j) * hscale) * tscale;
+        }
+        io.store<FA>(Tout, ldt, n0, v, nv);
+    }
+};
+template <class T>
+struct EpiRevS : EpiBase<EpiRevS<T>> {            // operand 0: h_l (sigma_{l-1})
+    using TF = Fw<T>;
+    static constexpr int FF = Fmt16<TF>::value;
+    static constexpr int kOps = 1;
+    float hscale; TF* Aout; int64_t lda;
+    template <int W> __device__ __forceinline__ void run(int64_t, int, const float*, int) const {}
+    __device__ __forceinline__ void chunk_smem(const WarpIO& io, int n0, float v[32], const msdf_tc::OpRow& r) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            uint32_t hw[4];
+            r.piece(0, p, hw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[8 * p + j] = v[8 * p + j] * sig_from_h<true>(WarpIO::unpack<FF>(hw, j) * hscale);
+        }
+        io.store<FF>(Aout, lda, n0, v, nv);
+    }
+};
+template <class T>
+struct EpiBwdS : EpiBase<EpiBwdS<T>> {            // operands: h_l, t_l, a_{l-1}
+    using TF = Fw<T>;
+    static constexpr int FF = Fmt16<TF>::value, FA = Fmt16<T>::value;
+    static constexpr int kOps = 3;
+    float hscale, inv_tscale, qscale; T* Pout; int64_t ldp;
+    template <int W> __device__ __forceinline__ void run(int64_t, int, const float*, int) const {}
+    __device__ __forceinline__ void chunk_smem(const WarpIO& io, int n0, float v[32], const msdf_tc::OpRow& r) const {
+        const int nv = this->chunk_cols(n0);
+        if (nv <= 0) return;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            uint32_t hw[4], tw[4], aw[4];
+            r.piece(0, p, hw);
+            r.piece(1, p, tw);
+            r.piece(2, p, aw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                v[8 * p + j] = EpiBwd<T>::template combine<true>(v[8 * p + j] * qscale, WarpIO::unpack<FF>(hw, j) * hscale, WarpIO::unpack<FA>(tw, j),
+                                                                 WarpIO::unpack<FF>(aw, j), inv_tscale);
+        }
+        io.store<FA>(Pout, ldp, n0, v, nv);
     }
 };
 template <class T>
@@ -1180,7 +1265,8 @@ struct Bufs {
     using TF = Fw<T>;
     TF* H[MSDF_MAX_LAYERS];  // H[0] = encoded input (ld d0p); H[l] = input of layer l (ld ldh)
     TF* A[MSDF_MAX_LAYERS];  // a_l (forward format), later z_l / pbar_l in the adjoint format T, in place  (l < L-1)
-    T *TG0, *T2[2], *Dout;
+    T *TG0, *T2[2], *Dout;     // T2: pbar ping-pong of the backward sweep
+    T* TL[MSDF_MAX_LAYERS];    // TL[l] = t_l, the tangent entering layer l (TL[0] = TG0); kept for the backward sweep
     float *G0, *G0b, *BH0, *dydx, *hashf, *sdf_raw, *mask, *dn, *dn_color, *gradc, *sdfc, *dcode;   // G0b: the skip layer's share of d sdf / d h0
     float *spec32, *dspec32;   // spec variant: specular head output / its adjoint, [Mc, 3]
     TF* X; TF* C[MSDF_MAX_LAYERS]; T* dC[2]; T* Hd;   // Hd: colour head dpre, [Mc, 64] (bf16 mode)
@@ -1261,6 +1347,8 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
             b.TG0 = c.take<T>(Mc, b.d0p);
             if (grid_feats) b.BH0 = c.take<float>(Mc, round_up(sn.d0, 4));
             b.T2[0] = c.take<T>(Mc, b.ldh); b.T2[1] = c.take<T>(Mc, b.ldh);
+            b.TL[0] = b.TG0;
+            for (int l = 1; l < sn.L; ++l) b.TL[l] = c.take<T>(Mc, b.ldh);
             b.ldo = padw<T>(sn.out[sn.L - 1]);
             b.Dout = c.take<T>(Mc, b.ldo);
             b.dn = c.take<float>(Mc, 3); b.dn_color = c.take<float>(Mc, 3);
@@ -1373,6 +1461,19 @@ int gemm_nn(const Ctx& c, const Net& n, int l, const TA* A, int64_t lda, int64_t
         return msdf_gemm::launch<kNN>(A, lda, n.W[l], n.ldw[l], Mc, n.in[l], n.out[l], 1, epi, c.st, what);
     }
 }
+// k_tc_stream launches (tensor-core mode): W_l for an "nt" product, W_l^T for an "nn" product, in A's format
+int g_stream_enabled = [] { const char* e = getenv("MSDF_STREAM"); return e ? atoi(e) : 1; }();
+template <class TA, class Epi, int kOps>
+int stream_gemm(const Ctx& c, const Net& n, int l, bool transposed, const TA* A, int64_t lda, int64_t Mc, const void* const (&R)[kOps],
+                const int (&rf)[kOps], const int64_t (&ldr)[kOps], Epi epi, const char* what, int ncols = 0) {
+    constexpr int fa = Fmt16<TA>::value;
+    const int rows = ncols > 0 ? ncols : (transposed ? n.in[l] : n.out[l]), kdim = transposed ? n.out[l] : n.in[l];
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(transposed ? n.wt(l, fa) : n.wk(l, fa));
+    const int kp = round_up(kdim, 64);
+    epi.N = rows;
+    return msdf_tc::launch_stream(A, fa, lda, Mc, kp, w, kp, round_up(rows, 16), R, rf, ldr, epi, c.st, what);
+}
+
 template <class T>
 int colsum(const Ctx& c, const T* X, int64_t ldx, const T* w, int64_t ws, int64_t Mc, int N, float* out);
 
@@ -1507,6 +1608,15 @@ int reverse_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc) {
             const int w = round_up(n.out[l], 64) - n.out[l];
             k_zero_cols<Fw<T>><<<nblk(Mc * w), 256, 0, c.st>>>(b.A[l], b.ldh, Mc, n.out[l], w);
             LAUNCHED("zero operand padding");
+        }
+        if constexpr (kIsBf16<T>) {
+            if (g_stream_enabled && l > 0 && l != n.skip && n.in[l] <= 256 && round_up(n.out[l], 64) <= 320) {
+                EpiRevS<T> es{};
+                es.hscale = in_scale(n, l); es.Aout = b.A[l - 1]; es.lda = b.ldh;
+                const void* const R[1] = {b.H[l]}; const int rf[1] = {Fmt16<Fw<T>>::value}; const int64_t ldr[1] = {b.ldh};
+                RUN((stream_gemm<Fw<T>, EpiRevS<T>, 1>(c, n, l, true, b.A[l], b.ldh, Mc, R, rf, ldr, es, "sdf reverse layer")));
+                continue;
+            }
         }
         RUN((gemm_nn<T>(c, n, l, b.A[l], b.ldh, Mc, make_rev<T>(n, b, l), "sdf reverse layer")));
     }
@@ -1650,24 +1760,34 @@ int color_backward(const Ctx& c, const Bufs<T>& b, int64_t Mc, const float* rgb,
 template <class T>
 int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, const msdf_mlp_grads* gr, float* grad_table) {
     const Net& n = c.sn;
-    // ---- tangent sweep (adjoint of the reverse sweep) with the a_l^T t_l weight gradients
-    T* Tin = b.TG0; int64_t ldt = b.d0p;
-    for (int l = 0; l < n.L - 1; ++l) {
+    const int L1 = n.L - 1;
+    // ---- tangent sweep (adjoint of the reverse sweep): t_{l+1} = (W_l t_l) sigma_l, every t_l kept
+    for (int l = 0; l < L1; ++l) {
+        T* Tin = b.TL[l]; const int64_t ldt = l == 0 ? b.d0p : b.ldh;
         if (l == n.skip) {
             k_skip_copy<T><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.TG0, b.d0p, Tin, ldt, Mc, n.d0, n.in[l] - n.d0, kInvSqrt2);
             LAUNCHED("tangent skip copy");
         }
-        RUN(wgrad<T>(c, b.A[l], b.ldh, Tin, ldt, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));   // a_l still in A[l]
-        T* Tout = b.T2[(l + 1) & 1];
-        EpiTan<T> e{};
-        e.Hn = b.H[l + 1]; e.ldh = b.ldh; e.hscale = in_scale(n, l + 1); e.AZ = b.A[l]; e.lda = b.ldh;
-        e.Tout = Tout; e.ldt = b.ldh; e.tscale = l + 1 == n.skip ? kInvSqrt2 : 1.0f;
-        RUN((gemm_nt<T>(c, n, l, Tin, ldt, Mc, 0, n.out[l], e, "sdf tangent layer")));
-        Tin = Tout; ldt = b.ldh;
+        bool streamed = false;
+        if constexpr (kIsBf16<T>) {
+            if (g_stream_enabled && round_up(n.in[l], 64) <= 320 && n.out[l] <= 256) {
+                EpiTanS<T> es{};
+                es.hscale = in_scale(n, l + 1); es.Tout = b.TL[l + 1]; es.ldt = b.ldh; es.tscale = l + 1 == n.skip ? kInvSqrt2 : 1.0f;
+                const void* const R[1] = {b.H[l + 1]}; const int rf[1] = {Fmt16<Fw<T>>::value}; const int64_t ldr[1] = {b.ldh};
+                RUN((stream_gemm<T, EpiTanS<T>, 1>(c, n, l, false, Tin, ldt, Mc, R, rf, ldr, es, "sdf tangent layer")));
+                streamed = true;
+            }
+        }
+        if (!streamed) {
+            EpiTan<T> e{};
+            e.Hn = b.H[l + 1]; e.ldh = b.ldh; e.hscale = in_scale(n, l + 1);
+            e.Tout = b.TL[l + 1]; e.ldt = b.ldh; e.tscale = l + 1 == n.skip ? kInvSqrt2 : 1.0f;
+            RUN((gemm_nt<T>(c, n, l, Tin, ldt, Mc, 0, n.out[l], e, "sdf tangent layer")));
+        }
     }
-    const int L1 = n.L - 1;
     const int out_last = n.out[L1];
     {
+        T* Tin = b.TL[L1]; const int64_t ldt = b.ldh;
         if (L1 == n.skip) {
             k_skip_copy<T><<<nblk(Mc * n.d0), 256, 0, c.st>>>(b.TG0, b.d0p, Tin, ldt, Mc, n.d0, n.in[L1] - n.d0, kInvSqrt2);
             LAUNCHED("tangent skip copy");
@@ -1684,21 +1804,54 @@ int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, con
             RUN(colsum<T>(c, b.Dout, b.ldo, nullptr, 0, Mc, out_last, gr->db[L1]));
         }
     }
+    // ---- backward sweep with both weight-gradient products of every layer: dW_l += pbar_l^T u_l + a_l^T t_l
     const T* P = b.Dout; int64_t ldp = b.ldo;
     for (int l = L1; l >= 0; --l) {
+        const int64_t ldin = l == 0 ? b.d0p : b.ldh;
         if (l < L1) {
-            RUN(wgrad<T>(c, P, ldp, b.H[l], l == 0 ? b.d0p : b.ldh, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, 0, gr->db[l]));
+            RUN(wgrad<T>(c, P, ldp, b.H[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, 0, gr->db[l]));
+            RUN(wgrad<T>(c, b.A[l], b.ldh, b.TL[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
         }
         if (l == 0 && !(c.grid && grad_table)) break;
+        if constexpr (kIsBf16<T>) {
+            // (the skip layer too when nothing reads the adjoint of its h_0 half: only the hidden columns are computed)
+            const bool skip_ok = l != n.skip || !(c.grid && grad_table);
+            if (g_stream_enabled && l > 0 && skip_ok && n.in[l] <= 256 && round_up(n.out[l], 64) <= 320) {
+                T* Pout = b.T2[l & 1];
+                EpiBwdS<T> es{};
+                es.hscale = in_scale(n, l); es.inv_tscale = l == n.skip ? kSqrt2 : 1.0f; es.qscale = l == n.skip ? kInvSqrt2 : 1.0f;
+                es.Pout = Pout; es.ldp = b.ldh;
+                const void* const R[3] = {b.H[l], b.TL[l], b.A[l - 1]};
+                const int rf[3] = {Fmt16<Fw<T>>::value, Fmt16<T>::value, Fmt16<Fw<T>>::value};
+                const int64_t ldr[3] = {ldin, ldin, b.ldh};
+                const int ncols = l == n.skip ? n.in[l] - n.d0 : n.in[l];
+                RUN((stream_gemm<T, EpiBwdS<T>, 3>(c, n, l, true, P, ldp, Mc, R, rf, ldr, es, "sdf backward layer", ncols)));
+                if (n.out[l - 1] % 64 != 0) {   // K padding of the next launch's operand must be finite (zero)
+                    const int w = round_up(n.out[l - 1], 64) - n.out[l - 1];
+                    k_zero_cols<T><<<nblk(Mc * w), 256, 0, c.st>>>(Pout, b.ldh, Mc, n.out[l - 1], w);
+                    LAUNCHED("zero operand padding");
+                }
+                P = Pout; ldp = b.ldh;
+                continue;
+            }
+        }
         EpiBwd<T> e{};
-        e.Hin = b.H[l]; e.ldh = l == 0 ? b.d0p : b.ldh; e.hscale = in_scale(n, l);
-        e.PZ = l > 0 ? b.adj(l - 1) : nullptr; e.ldp = b.ldh;
+        e.Hin = b.H[l]; e.ldh = ldin; e.hscale = in_scale(n, l);
+        e.Tin = b.TL[l]; e.ldt = ldin; e.inv_tscale = l == n.skip ? kSqrt2 : 1.0f;
+        e.Ain = l > 0 ? b.A[l - 1] : nullptr; e.lda = b.ldh;
+        T* Pout = b.T2[l & 1];
+        e.Pout = l > 0 ? Pout : nullptr; e.ldp = b.ldh;
         e.bh0 = (c.grid && grad_table) ? b.BH0 : nullptr; e.ldb = round_up(n.d0, 4);
         e.dh = l == n.skip ? n.in[l] - n.d0 : n.in[l];
         e.qscale = l == n.skip ? kInvSqrt2 : 1.0f;
         e.layer0 = l == 0; e.bh0_accum = n.skip > 0;
         RUN((gemm_nn<T>(c, n, l, P, ldp, Mc, e, "sdf backward layer")));
-        if (l > 0) { P = b.adj(l - 1); ldp = b.ldh; }
+        if (kIsBf16<T> && l > 0 && n.out[l - 1] % 64 != 0) {   // K padding of the next launch's operand must be finite (zero)
+            const int w = round_up(n.out[l - 1], 64) - n.out[l - 1];
+            k_zero_cols<T><<<nblk(Mc * w), 256, 0, c.st>>>(Pout, b.ldh, Mc, n.out[l - 1], w);
+            LAUNCHED("zero operand padding");
+        }
+        if (l > 0) { P = Pout; ldp = b.ldh; }
     }
     if (c.grid && grad_table) {
         const int64_t ldg = round_up(n.d0, 4);

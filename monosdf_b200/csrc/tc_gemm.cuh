@@ -300,6 +300,24 @@ struct WarpIO {
             }
         }
     }
+    // the two steps of unstage_packed() separately, for epilogues with several read-back operands that want to walk
+    // them 8 columns at a time instead of holding every operand's 16 packed words: stage() moves a prefetched block into
+    // the slot (or returns the cp.async landing buffer) and returns its address, piece() reads columns 8p .. 8p+7 of
+    // this lane's row.  Consecutive stage() calls alternate between the slot's two halves: at most two staged blocks
+    // are live; a __syncwarp() must separate the last piece() of a block from the second stage() after it.
+    __device__ __forceinline__ uint32_t stage(const uint4 q[4]) const {
+        if (amode) { async_ready(); return abuf_of(q); }
+        const uint32_t h = slot + flip;
+        flip ^= 2048u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
+        __syncwarp();
+        return h;
+    }
+    __device__ __forceinline__ void piece(uint32_t h, int p, uint32_t w[4]) const {
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(h + own[p]) : "memory");
+    }
     // same, but the row stays packed: w[p * 4 + j] holds columns p*8 + 2j (low half) and p*8 + 2j + 1 (high half)
     __device__ __forceinline__ void unstage_packed(const uint4 q[4], uint32_t w[16]) const {
         uint32_t h;
@@ -646,20 +664,24 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
                 const bool has_next = tile + gridDim.x < num_tiles;
                 mbar_wait(smem_u32(&bars->tfull[a]), aph);
                 tc_fence_after();
-                // accumulator chunks double buffered in registers like above (the 232-register budget pays for it)
-                uint32_t r[2][32];
-                if (half < chunks) tmem_ld32_issue(tacc + (uint32_t)half * 32u, r[0]);
+                // accumulator chunks double buffered in registers like above (the 232-register budget pays for it) -- except
+                // under an epilogue with three read-back operands, whose prefetch ring alone holds 96 registers
+                constexpr bool kAcc2 = Epi::kPre < 3;
+                uint32_t r[kAcc2 ? 2 : 1][32];
+                if (kAcc2 && half < chunks) tmem_ld32_issue(tacc + (uint32_t)half * 32u, r[0]);
 #pragma unroll 1
                 for (int ii = 0; ii < kMaxChunksPerWarp / kDepth; ++ii) {
 #pragma unroll
                     for (int k = 0; k < kDepth; ++k) {
                         const int c = half + 2 * (ii * kDepth + k);
                         if (c < chunks) {
-                            tmem_ld32_wait(r[k & 1]);
-                            if (c + 2 < chunks) tmem_ld32_issue(tacc + (uint32_t)(c + 2) * 32u, r[(k + 1) & 1]);
+                            constexpr int kb0 = kAcc2 ? 1 : 0;
+                            if (!kAcc2) tmem_ld32_issue(tacc + (uint32_t)c * 32u, r[0]);
+                            tmem_ld32_wait(r[k & kb0]);
+                            if (kAcc2 && c + 2 < chunks) tmem_ld32_issue(tacc + (uint32_t)(c + 2) * 32u, r[(k + 1) & kb0]);
                             float v[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[k & 1][j]);
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[k & kb0][j]);
                             io.amode = (k & 1) && use_async; io.qbase = pre[k];
                             epi.chunk(io, c * 32, v, pre[k]);
                         }
