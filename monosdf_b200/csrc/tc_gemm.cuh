@@ -192,6 +192,7 @@ struct WarpIO {
     uint32_t trn;       // slot offset of piece lane&3 of row lane/4 (global side); rows +8 are 512 bytes further
     int rows_left;      // M - row0, clamped to [0, 32]
     mutable uint32_t flip;   // bf16 stagings alternate between the two 2 KB halves of the slot: one __syncwarp each
+    uint32_t flip_mask;      // 2048; 0 for a 2 KB slot (k_tc_stream: a __syncwarp separates its consecutive stagings anyway)
     int64_t pf_row_shift;    // prefetch() addresses rows row0 + pf_row_shift (set while prefetching for the next tile)
     // Second prefetch path.  ptxas puts EVERY register prefetch (ld.global -> uint4) of the epilogue on one scoreboard
     // (tools/sass_scoreboards.py), so the staging store of a chunk waits for ALL outstanding loads, the refills issued
@@ -208,6 +209,7 @@ struct WarpIO {
         for (int p2 = 0; p2 < 4; ++p2) own[p2] = (uint32_t)(lane * 64 + ((p2 ^ x) << 4));
         trn = (uint32_t)(r * 64 + ((pc ^ ((r >> 1) & 3)) << 4));
         flip = 0u;
+        flip_mask = 2048u;
         pf_row_shift = 0;
         amode = 0;
         qbase = nullptr;
@@ -283,7 +285,7 @@ struct WarpIO {
             h = abuf_of(q);
         } else {
             h = slot + flip;
-            flip ^= 2048u;
+            flip ^= flip_mask;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
@@ -308,7 +310,7 @@ struct WarpIO {
     __device__ __forceinline__ uint32_t stage(const uint4 q[4]) const {
         if (amode) { async_ready(); return abuf_of(q); }
         const uint32_t h = slot + flip;
-        flip ^= 2048u;
+        flip ^= flip_mask;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
@@ -326,7 +328,7 @@ struct WarpIO {
             h = abuf_of(q);
         } else {
             h = slot + flip;
-            flip ^= 2048u;
+            flip ^= flip_mask;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + trn + (uint32_t)i * 512u), "r"(q[i].x), "r"(q[i].y), "r"(q[i].z), "r"(q[i].w) : "memory");
@@ -370,7 +372,7 @@ struct WarpIO {
     __device__ __forceinline__ void store_packed(void* Pv, int64_t ld, int n0, const uint32_t w[16], int nvalid) const {
         uint16_t* P = reinterpret_cast<uint16_t*>(Pv);
         const uint32_t h = slot + flip;
-        flip ^= 2048u;
+        flip ^= flip_mask;
 #pragma unroll
         for (int p = 0; p < 4; ++p)
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(h + own[p]), "r"(w[4 * p]), "r"(w[4 * p + 1]), "r"(w[4 * p + 2]), "r"(w[4 * p + 3]) : "memory");

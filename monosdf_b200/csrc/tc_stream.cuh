@@ -12,8 +12,8 @@
 // transpose.  Room for the rings comes from streaming the layer's weights per 64-column k-block with the A tile (they are
 // L2 resident: +128 KB of L2 -> SM traffic per 128-row tile) instead of keeping all of them resident in shared memory.
 //
-// 384 threads: warp 0 = A / W producer, warp 1 = MMA issuer (tcgen05.mma 128 x N x 16, double-buffered TMEM
-// accumulators), warp 2 = read-back operand producer, warps 4-11 = epilogue (232 registers).
+// 640 threads: warp 0 = A / W producer, warp 1 = MMA issuer (tcgen05.mma 128 x N x 16, double-buffered TMEM
+// accumulators), warp 2 = read-back operand producer, warps 4-19 = epilogue (no prefetch rings to hold: 104 registers do).
 #pragma once
 #include <stdlib.h>
 
@@ -22,8 +22,12 @@
 namespace msdf_tc {
 
 constexpr int kMaxOps = 3;
+constexpr int kStreamEpiWarps = 16;                       // 4 per TMEM lane quadrant: group g takes chunks g and g + 4
+constexpr int kStreamThreads = (4 + kStreamEpiWarps) * 32;
+constexpr int kStreamRegsLight = 40, kStreamRegsEpi = 104;  // 128 x 40 + 512 x 104 <= 640 x 96 (the launch allocation)
 constexpr int kMaxBoxes = 4;
 constexpr uint32_t kBoxBytes = BM * 128;                 // 128 rows x 64 columns x 2 bytes
+constexpr uint32_t kStreamSlot = 2048;                   // per epilogue warp: one 32 x 32 block of 16-bit values
 
 struct StreamBarriers {
     uint64_t sfull[2], sempty[2], tfull[2], tempty[2], ofull[kMaxOps][kMaxBoxes], oempty[kMaxOps][kMaxBoxes];
@@ -46,7 +50,7 @@ struct OpRow {
 
 // Epilogue concept (beside N, colvec()): static constexpr int kOps; void chunk_smem(const WarpIO&, int n0, float v[32], const OpRow&) const
 template <class Epi>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kStreamThreads, 1)
 k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ OpMaps ops,
             int64_t M, int BN, int KB, int nboxes, int a_fmt, Epi epi) {
     extern __shared__ uint8_t smem_raw[];
@@ -57,10 +61,10 @@ k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const uint32_t stage_bytes = kStageBytesA + w_block;        // A k-block + W k-block
     const uint32_t sS = base;                                   // 2 stages
     const uint32_t sO = sS + 2u * stage_bytes;                  // kOps x nboxes boxes
-    const uint32_t sE = sO + (uint32_t)(kOps * nboxes) * kBoxBytes;   // kEpiWarps staging slots (output stores)
-    const uint32_t sV = sE + kEpiWarps * kSlotBytes;            // per-column vector, 256 floats
+    const uint32_t sE = sO + (uint32_t)(kOps * nboxes) * kBoxBytes;   // staging slots of the epilogue warps (output stores): 2 KB each
+    const uint32_t sV = sE + kStreamEpiWarps * kStreamSlot;     // per-column vector, 256 floats
     StreamBarriers* bars = reinterpret_cast<StreamBarriers*>(gen_base + 2u * stage_bytes + (size_t)(kOps * nboxes) * kBoxBytes +
-                                                             kEpiWarps * kSlotBytes + kColVecBytes);
+                                                             kStreamEpiWarps * kStreamSlot + kColVecBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t num_tiles = (M + BM - 1) / BM;
     const int chunks = (BN + 31) / 32;
@@ -70,9 +74,9 @@ k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         tma_prefetch_desc(&mapA);
         tma_prefetch_desc(&mapW);
         for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&bars->sfull[s]), 1); mbar_init(smem_u32(&bars->sempty[s]), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars->tfull[a]), 1); mbar_init(smem_u32(&bars->tempty[a]), kEpiWarps * 32); }
+        for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&bars->tfull[a]), 1); mbar_init(smem_u32(&bars->tempty[a]), kStreamEpiWarps * 32); }
         for (int o = 0; o < kMaxOps; ++o)
-            for (int b = 0; b < kMaxBoxes; ++b) { mbar_init(smem_u32(&bars->ofull[o][b]), 1); mbar_init(smem_u32(&bars->oempty[o][b]), kEpiWarps); }
+            for (int b = 0; b < kMaxBoxes; ++b) { mbar_init(smem_u32(&bars->ofull[o][b]), 1); mbar_init(smem_u32(&bars->oempty[o][b]), kStreamEpiWarps); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(smem_u32(&bars->tmem_base), kTmemCols);
@@ -90,7 +94,7 @@ k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegsLight));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kStreamRegsLight));
         if (warp == 0) {
             if (lane == 0) {
                 // ---- producer 1: per tile and k-block the A tile's and the weights' 64 columns
@@ -152,15 +156,17 @@ k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             __syncwarp();
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegsEpi));
-        // ---- epilogue: TMEM lane quadrant = warp % 4; the two warps of a quadrant take the even / odd 32-column chunks
-        const int q = warp & 3, half = (warp - 4) >> 2;
-        WarpIO io{sE + (uint32_t)(warp - 4) * kSlotBytes, lane, (int64_t)blockIdx.x * BM + q * 32, M, sV};
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kStreamRegsEpi));
+        // ---- epilogue: TMEM lane quadrant = warp % 4; the four warps of a quadrant take chunks g and g + 4 (g = group);
+        // every warp follows every operand box (waits for it, releases it) so that the ring's phases stay in step
+        const int q = warp & 3, g4 = (warp - 4) >> 2;
+        WarpIO io{sE + (uint32_t)(warp - 4) * kStreamSlot, lane, (int64_t)blockIdx.x * BM + q * 32, M, sV};
         io.init();
         io.abuf = 0u;
+        io.flip_mask = 0u;                                       // 2 KB slot: no alternation (a __syncwarp follows every chunk)
         OpRow orow;
         orow.sw = (uint32_t)(lane & 7);                          // (q * 32 + lane) & 7
-        orow.pc0 = (uint32_t)half * 4u;
+        orow.pc0 = (uint32_t)(g4 & 1) * 4u;
         const uint32_t rowoff = (uint32_t)(q * 32 + lane) * 128u;
         uint32_t it = 0, g = 0;
         for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
@@ -169,27 +175,26 @@ k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + a * 256u;
             mbar_wait(smem_u32(&bars->tfull[a]), aph);
             tc_fence_after();
-            uint32_t r[2][32];
-            if (half < chunks) tmem_ld32_issue(tacc + (uint32_t)half * 32u, r[0]);
 #pragma unroll 1
             for (int bb = 0; bb < nbx; bb += 2) {
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
                     const int b = bb + k;
                     if (b >= nbx) break;
-                    const int c = 2 * b + half;
+                    // box b holds chunks 2b, 2b+1: they belong to groups (2b) % 4 and (2b+1) % 4, i.e. to this warp iff
+                    // (b & 1) == (g4 >> 1); its chunk is then 2b + (g4 & 1) = g4 + 4 (b >> 1)
+                    const bool mine = (b & 1) == (g4 >> 1);
+                    const int c = 2 * b + (g4 & 1);
                     const uint32_t slot = (g + (uint32_t)k) % (uint32_t)nboxes, ph = ((g + (uint32_t)k) / (uint32_t)nboxes) & 1u;
 #pragma unroll
                     for (int o = 0; o < kOps; ++o) {
                         mbar_wait(smem_u32(&bars->ofull[o][slot]), ph);
                         orow.row[o] = sO + (uint32_t)(o * nboxes + (int)slot) * kBoxBytes + rowoff;
                     }
-                    if (c < chunks) {
-                        tmem_ld32_wait(r[k]);
-                        if (c + 2 < chunks) tmem_ld32_issue(tacc + (uint32_t)(c + 2) * 32u, r[k ^ 1]);
+                    if (mine && c < chunks) {
+                        // (the other three warps of the scheduler hide the TMEM latency: no register double buffer)
                         float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[k][j]);
+                        tmem_ld32(tacc + (uint32_t)c * 32u, v);
                         epi.chunk_smem(io, c * 32, v, orow);
                     }
                     // this warp is done with the boxes (chunk_smem reads its operands before it stores)
@@ -230,7 +235,7 @@ int launch_stream(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, cons
     for (int o = 0; o < kOps; ++o) { rc = make_map(&ops.m[o], R[o], r_fmt[o], M, cols, ldr[o], BM, what); if (rc) return rc; }
     const int KB = Kp / 64;
     const size_t stage_bytes = kStageBytesA + (size_t)BN * 128;
-    const size_t fixed = 1024 + sizeof(StreamBarriers) + kEpiWarps * kSlotBytes + kColVecBytes + 2 * stage_bytes;
+    const size_t fixed = 1024 + sizeof(StreamBarriers) + kStreamEpiWarps * kStreamSlot + kColVecBytes + 2 * stage_bytes;
     int nboxes = kOps > 0 ? (int)((227 * 1024 - fixed) / ((size_t)kOps * kBoxBytes)) : 0;
     if (nboxes > kMaxBoxes) nboxes = kMaxBoxes;
     { static const int cap = [] { const char* e = getenv("MSDF_STREAM_BOXES"); return e ? atoi(e) : kMaxBoxes; }(); if (nboxes > cap && cap >= 2) nboxes = cap; }   // experiment knob: ring depth
@@ -246,7 +251,7 @@ int launch_stream(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, cons
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
                                      (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(kOps + Epi::kStores)));
-    k_tc_stream<Epi><<<grid, kGemmThreads, smem, st>>>(mA, mW, ops, M, BN, KB, nboxes, a_fmt, epi);
+    k_tc_stream<Epi><<<grid, kStreamThreads, smem, st>>>(mA, mW, ops, M, BN, KB, nboxes, a_fmt, epi);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
