@@ -1809,8 +1809,21 @@ int sdf_backward(const Ctx& c, const Bufs<T>& b, const float* x, int64_t Mc, con
     for (int l = L1; l >= 0; --l) {
         const int64_t ldin = l == 0 ? b.d0p : b.ldh;
         if (l < L1) {
-            RUN(wgrad<T>(c, P, ldp, b.H[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, 0, gr->db[l]));
-            RUN(wgrad<T>(c, b.A[l], b.ldh, b.TL[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+            bool paired = false;
+            if constexpr (kIsBf16<T>) {
+                if (g_stream_enabled) {     // both products of the layer in one launch (one prologue, one flush of dW_l)
+                    EpiAtomic e{};
+                    e.N = n.in[l]; e.C = gr->dW[l]; e.ldc = n.ldw[l]; e.Mrows = n.out[l]; e.perm_rows = 0; e.perm_shift = 1; e.col_rot = 0;
+                    RUN(msdf_tc::launch_wgrad(P, Fmt16<T>::value, ldp, round_up(n.out[l], 64), b.H[l], Fmt16<Fw<T>>::value, ldin,
+                                              round_up(n.in[l], 64), Mc, e, c.st, "weight gradient (both products)", gr->db[l], n.out[l], 0, 1,
+                                              b.A[l], Fmt16<Fw<T>>::value, b.ldh, b.TL[l], Fmt16<T>::value, ldin));
+                    paired = true;
+                }
+            }
+            if (!paired) {
+                RUN(wgrad<T>(c, P, ldp, b.H[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0, 0, gr->db[l]));
+                RUN(wgrad<T>(c, b.A[l], b.ldh, b.TL[l], ldin, n.out[l], n.in[l], Mc, gr->dW[l], n.ldw[l], 0));
+            }
         }
         if (l == 0 && !(c.grid && grad_table)) break;
         if constexpr (kIsBf16<T>) {

@@ -720,7 +720,10 @@ template <class Epi>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int nbx_, int BJ,
            int64_t rows_per_split, int stages, int x_fmt, int y_fmt, Epi epi, float* __restrict__ colsum, int colsum_n,
-           int colsum_perm, int colsum_shift) {
+           int colsum_perm, int colsum_shift, const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapY2,
+           int x_fmt2, int y_fmt2, int phases) {
+    // phases == 2: dW += X^T Y + X2^T Y2 in ONE launch (the two weight-gradient products of a layer, pbar^T h and a^T t:
+    // same tile geometry, one prologue, one flush of the accumulator); the second product's k-blocks follow the first's
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
@@ -767,13 +770,17 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            if (phases > 1) { tma_prefetch_desc(&mapX2); tma_prefetch_desc(&mapY2); }
+            for (int kk = 0; kk < nkb * phases; ++kk) {
+                const int kb = kk >= nkb ? kk - nkb : kk;
                 mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
                 mbar_expect_tx(smem_u32(&bars->full[s]), stage_bytes);
                 const uint32_t st = base + s * stage_bytes;
                 const int row = (int)(r0 + (int64_t)kb * 64);
-                for (uint32_t b = 0; b < nbx; ++b) tma_load_2d(st + b * kBox, &mapX, smem_u32(&bars->full[s]), i0 + (int)b * 64, row);
-                for (uint32_t b = 0; b < nby; ++b) tma_load_2d(st + (nbx + b) * kBox, &mapY, smem_u32(&bars->full[s]), j0 + (int)b * 64, row);
+                const CUtensorMap* mx = kk >= nkb ? &mapX2 : &mapX;
+                const CUtensorMap* my = kk >= nkb ? &mapY2 : &mapY;
+                for (uint32_t b = 0; b < nbx; ++b) tma_load_2d(st + b * kBox, mx, smem_u32(&bars->full[s]), i0 + (int)b * 64, row);
+                for (uint32_t b = 0; b < nby; ++b) tma_load_2d(st + (nbx + b) * kBox, my, smem_u32(&bars->full[s]), j0 + (int)b * 64, row);
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
@@ -782,7 +789,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         if (lane == 0 && nkb > 0) {
             const uint32_t idesc = instr_desc(128, BJ, 1, 1, mma_fmt, mma_fmt);
             int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb * phases; ++kb) {
                 mbar_wait(smem_u32(do_conv ? &bars->conv[s] : &bars->full[s]), ph);
                 tc_fence_after();
                 const uint32_t st = base + s * stage_bytes;
@@ -814,12 +821,13 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             const int pi = t % pairs, g = t / pairs;
             const int c = (pi & 31) * 2;
             const uint32_t box_off = (uint32_t)(pi >> 5) * kBox;
-            const uint32_t conv_off = x_fmt == kF16 ? 0u : nbx * kBox;
-            const int conv_vecs = (int)((x_fmt == kF16 ? nbx : nby) * (kBox / 16u));
             const bool x_bf16 = do_conv || x_fmt == kBF16;          // format of X once the stage is released
             float s0 = 0.f, s1 = 0.f;
             int s = 0; uint32_t ph = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kk = 0; kk < nkb * phases; ++kk) {
+                const int xf = kk >= nkb ? x_fmt2 : x_fmt;            // the fp16 operand of this k-block's product
+                const uint32_t conv_off = xf == kF16 ? 0u : nbx * kBox;
+                const int conv_vecs = (int)((xf == kF16 ? nbx : nby) * (kBox / 16u));
                 if (lane == 0) mbar_wait(smem_u32(&bars->full[s]), ph);   // one poller per warp
                 __syncwarp();
                 if (do_conv) {
@@ -839,13 +847,15 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 }
                 if (do_colsum) {
                     const uint32_t st = base + s * stage_bytes + box_off;
+                    if (kk < nkb) {                                 // (the second product's X has no bias attached)
 #pragma unroll 16
-                    for (int kk = 0; kk < rpg; ++kk) {
-                        const int k = g * rpg + kk;
+                    for (int kr = 0; kr < rpg; ++kr) {
+                        const int k = g * rpg + kr;
                         uint32_t w;
                         asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(st + (uint32_t)(k * 128 + ((((c >> 3) ^ (k & 7)) << 4) | ((c & 7) * 2)))) : "memory");
                         s0 += x_bf16 ? WarpIO::lo_of<kBF16>(w) : WarpIO::lo_of<kF16>(w);
                         s1 += x_bf16 ? WarpIO::hi_of<kBF16>(w) : WarpIO::hi_of<kF16>(w);
+                    }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(smem_u32(&bars->empty[s]));
@@ -967,16 +977,27 @@ int launch_gemm(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, const 
 // of 64); the functor masks i / j beyond the real sizes and accumulates atomically.
 template <class Epi>
 int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, int y_fmt, int64_t ldy, int Cj, int64_t M, const Epi& epi,
-                 cudaStream_t st, const char* what, float* colsum = nullptr, int colsum_n = 0, int colsum_perm = 0, int colsum_shift = 1) {
+                 cudaStream_t st, const char* what, float* colsum = nullptr, int colsum_n = 0, int colsum_perm = 0, int colsum_shift = 1,
+                 const void* X2 = nullptr, int x_fmt2 = 0, int64_t ldx2 = 0, const void* Y2 = nullptr, int y_fmt2 = 0, int64_t ldy2 = 0) {
     if (M <= 0) return MSDF_OK;
+    if (X2 != nullptr && ((x_fmt != y_fmt) != (x_fmt2 != y_fmt2) || x_fmt == y_fmt)) {
+        msdf_set_error("%s: a two-product weight gradient needs two mixed-format products", what);
+        return MSDF_ERR_ARG;
+    }
     if (Ci % 64 != 0 || Cj % 64 != 0 || Ci <= 0 || Cj <= 0) { msdf_set_error("%s: wgrad needs column counts %% 64 == 0", what); return MSDF_ERR_ARG; }
     if (colsum != nullptr && x_fmt != y_fmt && x_fmt == kF16) {
         msdf_set_error("%s: column sums of the fp16 operand of a mixed-format weight gradient are not supported", what);
         return MSDF_ERR_UNSUPPORTED;
     }
-    CUtensorMap mX, mY;
+    CUtensorMap mX, mY, mX2, mY2;
     int rc = make_map(&mX, X, x_fmt, M, Ci, ldx, 64, what); if (rc) return rc;
     rc = make_map(&mY, Y, y_fmt, M, Cj, ldy, 64, what); if (rc) return rc;
+    mX2 = mX; mY2 = mY;
+    if (X2 != nullptr) {
+        rc = make_map(&mX2, X2, x_fmt2, M, Ci, ldx2, 64, what); if (rc) return rc;
+        rc = make_map(&mY2, Y2, y_fmt2, M, Cj, ldy2, 64, what); if (rc) return rc;
+    }
+    const int phases = X2 != nullptr ? 2 : 1;
     const int BJ = Cj < 256 ? Cj : 256;
     const int nbx = Ci > 128 ? 4 : 2;                       // X tile of 256 (two accumulators) or 128 columns
     const int it = (Ci + nbx * 64 - 1) / (nbx * 64), jt = (Cj + BJ - 1) / BJ;
@@ -997,8 +1018,9 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
         attr_set = true;
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)Ci * (double)Cj, st, (double)M * 2.0 * (double)(Ci + Cj));
-    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, nbx, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift);
+    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * phases * (double)M * (double)Ci * (double)Cj, st, phases * (double)M * 2.0 * (double)(Ci + Cj));
+    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, nbx, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift,
+                                                  mX2, mY2, x_fmt2, y_fmt2, phases);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
