@@ -31,7 +31,8 @@ constexpr int BM = 128;            // rows per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = (2 + kEpiWarps) * 32;        // k_tc_wgrad: producer warp, MMA warp, 8 epilogue warps
+constexpr int kWgEpiWarps = 16;                       // k_tc_wgrad: producer warp, MMA warp, 16 converter / epilogue warps (the
+constexpr int kWgThreads = (2 + kWgEpiWarps) * 32;    // conversion and the bias sums are issue-latency bound: 2 warps per scheduler were not enough)
 constexpr int kGemmThreads = (4 + kEpiWarps) * 32;    // k_tc_gemm: warpgroup 0 = {producer, MMA, 2 idle warps}, then 8 epilogue warps
 constexpr int kRegsLight = 40, kRegsEpi = 232;        // setmaxnreg split of k_tc_gemm: 128 x 40 + 256 x 232 = 384 x 168
 constexpr int kMaxStages = 8;
@@ -717,7 +718,7 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 // below), so the 256-column X tile matters: the Y boxes are written / converted once for two accumulators' worth of
 // MMAs (per 128x256 unit of work 112 KB instead of 160 KB of shared-memory traffic in the mixed-format products).
 template <class Epi>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kWgThreads, 1)
 k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int nbx_, int BJ,
            int64_t rows_per_split, int stages, int x_fmt, int y_fmt, Epi epi, float* __restrict__ colsum, int colsum_n,
            int colsum_perm, int colsum_shift, const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapY2,
@@ -731,8 +732,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     const uint32_t nbx = (uint32_t)nbx_, nby = (uint32_t)BJ / 64u;
     const uint32_t tmem_cols = nbx > 2 ? 512u : 256u;
     const uint32_t stage_bytes = (nbx + nby) * kBox;
-    const uint32_t sE = base + (uint32_t)stages * stage_bytes;
-    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)stages * stage_bytes + kEpiWarps * kSlotBytes);
+    const uint32_t sE = base;   // the flush's staging slots reuse the stage ring (idle by then; host: ring >= 16 slots)
+    Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int i0 = blockIdx.x * (int)(nbx * 64u), j0 = blockIdx.y * BJ;
     const int64_t r0 = (int64_t)blockIdx.z * rows_per_split;
@@ -744,8 +745,9 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     // read and a write of the fp16 boxes: 128 / 160 KB, measured 1.7x per launch).  Tried and rejected: the epilogue
     // warps loading the fp16 operand with LDG two stages ahead and writing the swizzled boxes themselves (96 KB of
     // shared-memory traffic again, but 64 KB of loads in flight per SM is more than the LSU path sustains: 2.2x).
+    // Also tried: the instruction descriptor has separate format fields for A and B, but a kind::f16 MMA with one fp16
+    // and one bf16 operand traps on sm_100a ("an illegal instruction was encountered"), so the conversion stays.
     const bool do_conv = x_fmt != y_fmt;
-    const int mma_fmt = do_conv ? (int)kBF16 : x_fmt;
     const int nkb = r1 > r0 ? (int)((r1 - r0 + 63) / 64) : 0;   // the last block of a split may run past r1: the host
                                                                  // makes rows_per_split a multiple of 64, so only the
                                                                  // global tail is ragged and TMA zero-fills it
@@ -755,8 +757,8 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         // a stage is released by the MMA commit and, when the column sums of X ride along, by the 8 reducing warps
         for (int s = 0; s < stages; ++s) {
             mbar_init(smem_u32(&bars->full[s]), 1);
-            mbar_init(smem_u32(&bars->empty[s]), do_colsum ? 1 + kEpiWarps : 1);
-            mbar_init(smem_u32(&bars->conv[s]), kEpiWarps);
+            mbar_init(smem_u32(&bars->empty[s]), do_colsum ? 1 + kWgEpiWarps : 1);
+            mbar_init(smem_u32(&bars->conv[s]), kWgEpiWarps);
         }
         mbar_init(smem_u32(&bars->tfull[0]), 1);
         fence_barrier_init();
@@ -787,6 +789,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
         __syncwarp();
     } else if (warp == 1) {
         if (lane == 0 && nkb > 0) {
+            const int mma_fmt = do_conv ? (int)kBF16 : x_fmt;
             const uint32_t idesc = instr_desc(128, BJ, 1, 1, mma_fmt, mma_fmt);
             int s = 0; uint32_t ph = 0;
             for (int kb = 0; kb < nkb * phases; ++kb) {
@@ -817,7 +820,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             // Thread t: column pair t % (32 nbx) of the X tile, k-rows rpg (t / (32 nbx)) .. + rpg - 1 of the 64-row block
             // (rpg = 16 for the 128-column tile, 32 for the 256-column tile); a warp reads whole 128-byte swizzle rows.
             const int t = (int)threadIdx.x - 64;
-            const int pairs = (int)nbx * 32, rpg = 64 / (kEpiWarps * 32 / pairs);
+            const int pairs = (int)nbx * 32, rpg = 64 / (kWgEpiWarps * 32 / pairs);
             const int pi = t % pairs, g = t / pairs;
             const int c = (pi & 31) * 2;
             const uint32_t box_off = (uint32_t)(pi >> 5) * kBox;
@@ -832,12 +835,25 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 __syncwarp();
                 if (do_conv) {
                     const uint32_t cb = base + s * stage_bytes + conv_off;
-                    for (int i = t; i < conv_vecs; i += kEpiWarps * 32) {
-                        uint32_t w[4];
-                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(cb + (uint32_t)i * 16u) : "memory");
+                    // all of a thread's vectors are loaded before the first is converted: one shared-memory latency per
+                    // stage instead of one per vector (ncu source page, one vector per trip: 32 % of the kernel's samples
+                    // on the first conversion after the LDS.128, short scoreboard)
+                    constexpr int kConvU = 4;                       // 4 boxes x 512 vectors / 512 threads
+                    uint32_t w[kConvU][4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) w[j] = WarpIO::pack2<kBF16>(WarpIO::lo_of<kF16>(w[j]), WarpIO::hi_of<kF16>(w[j]));
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cb + (uint32_t)i * 16u), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                    for (int u = 0; u < kConvU; ++u) {
+                        const int i = t + u * kWgEpiWarps * 32;
+                        if (i < conv_vecs)
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]) : "r"(cb + (uint32_t)i * 16u) : "memory");
+                    }
+#pragma unroll
+                    for (int u = 0; u < kConvU; ++u) {
+                        const int i = t + u * kWgEpiWarps * 32;
+                        if (i < conv_vecs) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) w[u][j] = WarpIO::pack2<kBF16>(WarpIO::lo_of<kF16>(w[u][j]), WarpIO::hi_of<kF16>(w[u][j]));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(cb + (uint32_t)i * 16u), "r"(w[u][0]), "r"(w[u][1]), "r"(w[u][2]), "r"(w[u][3]) : "memory");
+                        }
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -869,15 +885,17 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 if (col + 1 < colsum_n) atomicAdd(colsum + (colsum_perm > 0 ? (col + 1 + colsum_shift) % colsum_perm : col + 1), s1);
             }
         }
-        const int q = warp & 3, half = (warp - 2) >> 2;
+        const int q = warp & 3, grp = (warp - 2) >> 2;
         const int chunks = (BJ + 31) / 32;
         mbar_wait(smem_u32(&bars->tfull[0]), 0);
         tc_fence_after();
+        // every MMA has read its stage; the barrier also ends the other warps' bias sums out of the last stage
+        asm volatile("bar.sync 1, %0;" ::"n"(kWgEpiWarps * 32) : "memory");
         WarpIO io{sE + (uint32_t)(warp - 2) * kSlotBytes, lane, (int64_t)i0 + q * 32, (int64_t)1 << 40, 0u};
         io.init();
         for (uint32_t h = 0; h < nbx / 2; ++h) {
             io.retile((int64_t)i0 + h * 128 + q * 32);
-            for (int c = half; c < chunks; c += 2) {
+            for (int c = grp; c < chunks; c += kWgEpiWarps / 4) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + h * 256u + (uint32_t)c * 32u, v);
                 epi.chunk(io, j0 + c * 32, v, nullptr);
@@ -1007,9 +1025,10 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     if (rps < 256) rps = 256;
     splits = (int)((M + rps - 1) / rps);
     const uint32_t stage_bytes = (nbx + BJ / 64) * 64 * 128;
-    const size_t fixed = 1024 + sizeof(Barriers) + kEpiWarps * kSlotBytes;
+    const size_t fixed = 1024 + sizeof(Barriers);
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
     if (stages > 6) stages = 6;
+    if ((size_t)stages * stage_bytes < (size_t)kWgEpiWarps * kSlotBytes) { msdf_set_error("%s: stage ring smaller than the flush slots", what); return MSDF_ERR_ARG; }
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     static bool attr_set = false;
     if (!attr_set) {
@@ -1019,7 +1038,7 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * phases * (double)M * (double)Ci * (double)Cj, st, phases * (double)M * 2.0 * (double)(Ci + Cj));
-    k_tc_wgrad<Epi><<<grid, kThreads, smem, st>>>(mX, mY, M, nbx, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift,
+    k_tc_wgrad<Epi><<<grid, kWgThreads, smem, st>>>(mX, mY, M, nbx, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift,
                                                   mX2, mY2, x_fmt2, y_fmt2, phases);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
