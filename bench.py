@@ -190,7 +190,20 @@ def run_reference(args):
     os.environ["CUDA_VISIBLE_DEVICES"] = ""          # host cores only: the reference's hard-coded .cuda() calls become no-ops
     cores = args.cpu_threads or os.cpu_count() or 1
     n = args.cpu_rays
-    t, kind = cpu_reference_step_time(args.beta, n, args.steps, args.warmup, cores)
+    # the reference's constructors and loss print to stdout (network.py / loss.py); the contract is ONE JSON line there
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        t, kind = cpu_reference_step_time(args.beta, n, args.steps, args.warmup, cores)
+        t1 = None
+        if not args.cpu_threads and cores > 1:
+            # the reference trainer itself runs with torch.set_num_threads(1) (monosdf_train.py:37): one bounded step of that too
+            t1, _ = cpu_reference_step_time(args.beta, n, 1, 1, 1)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
     v = n / t
     what = "the reference's own model/network.py + model/loss.py + torch.optim.Adam" if kind == "reference" else \
         "oracle/port.py (restatement of the reference, pinned by tests/test_oracle_golden.py) + torch.optim.Adam"
@@ -205,9 +218,7 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    if not args.cpu_threads and cores > 1:
-        # the reference trainer itself runs with torch.set_num_threads(1) (monosdf_train.py:37): one bounded step of that too
-        t1, _ = cpu_reference_step_time(args.beta, n, 1, 1, 1)
+    if t1 is not None:
         line["cpu_baseline_1thread"] = {"value": n / t1, "unit": UNIT, "cores": 1, "kind": kind,
                                         "sample": "one timed %d-ray step after one warm-up, 1 thread (monosdf_train.py:37)" % n}
     print(json.dumps(line))
@@ -580,12 +591,12 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor",
                      "kernel": "k_gemm (fp32 SIMT MLP sweeps)" if gemm_cls == 0 else
-                               "tcgen05 kernels: k_fused_sdf (sampler passes) + k_tc_gemm (per-layer sweeps) + k_tc_wgrad",
+                               "tcgen05 kernels: k_fused_sdf (sampler passes, training forward) + k_tc_stream / k_tc_gemm (per-layer sweeps) + k_tc_wgrad",
                      # achieved = ALGORITHMIC FLOPs of one step (SURVEY 8d per-ray figure at the measured sampler rounds x rays)
                      # / the time one step spends in those kernels (CUDA events per launch, mean of the instrumented steps)
                      "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                     "traffic": traffic, "traffic_note": "ncu dram bytes per launch of the class's largest kernel (k_tc_gemm<EpiTan>, 262144 "
-                                                          "rows; algorithmic 671 MB); per-kernel table: profiles/ncu_traffic.json",
+                     "traffic": traffic, "traffic_note": "ncu dram bytes per launch of the class's largest kernel (k_tc_wgrad, both products of "
+                                                          "a layer, 262144 rows; algorithmic 537 MB); per-kernel table: profiles/ncu_traffic.json",
                      "peak_source": peak_src,
                      "algorithmic_gflop_per_ray": gflop_per_ray(args.config, rounds), "rays_per_step_per_gpu": n,
                      "launches": g_n, "kernel_ms_per_step": g_ms, "instrumented_step_ms": t_prof,
