@@ -977,16 +977,27 @@ struct EpiTanS : EpiBase<EpiTanS<T>> {            // operand 0: h_{l+1}
         io.store<FA>(Tout, ldt, n0, v, nv);
     }
 };
-template <class T>
-struct EpiRevS : EpiBase<EpiRevS<T>> {            // operand 0: h_l (sigma_{l-1})
+template <class T, bool kG0 = false>
+struct EpiRevS : EpiBase<EpiRevS<T, kG0>> {       // operand 0: h_l (sigma_{l-1})
     using TF = Fw<T>;
     static constexpr int FF = Fmt16<TF>::value;
     static constexpr int kOps = 1;
     float hscale; TF* Aout; int64_t lda;
+    // kG0: columns >= dh are d sdf / d h0 (the h0 half of the skip concat; all of layer 0: dh = 0) and leave as fp32
+    // rows of g0; both halves of the skip layer carry its 1/sqrt2
+    int dh; float qscale; float* g0; int64_t ldg;
     template <int W> __device__ __forceinline__ void run(int64_t, int, const float*, int) const {}
     __device__ __forceinline__ void chunk_smem(const WarpIO& io, int n0, float v[32], const msdf_tc::OpRow& r) const {
         const int nv = this->chunk_cols(n0);
         if (nv <= 0) return;
+        int nh = nv;
+        if constexpr (kG0) {
+            nh = dh - n0 < nv ? dh - n0 : nv;         // hidden columns of this chunk
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= qscale;
+            if (nh < nv) io.store_f32_narrow(g0, ldg, n0 - dh, v, nh > 0 ? nh : 0, nv);
+            if (nh <= 0) return;
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
             uint32_t hw[4];
@@ -994,7 +1005,7 @@ struct EpiRevS : EpiBase<EpiRevS<T>> {            // operand 0: h_l (sigma_{l-1}
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[8 * p + j] = v[8 * p + j] * sig_from_h<true>(WarpIO::unpack<FF>(hw, j) * hscale);
         }
-        io.store<FF>(Aout, lda, n0, v, nv);
+        io.store<FF>(Aout, lda, n0, v, nh);
     }
 };
 template <class T>
@@ -1610,11 +1621,21 @@ int reverse_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc) {
             LAUNCHED("zero operand padding");
         }
         if constexpr (kIsBf16<T>) {
-            if (g_stream_enabled && l > 0 && l != n.skip && n.in[l] <= 256 && round_up(n.out[l], 64) <= 320) {
-                EpiRevS<T> es{};
-                es.hscale = in_scale(n, l); es.Aout = b.A[l - 1]; es.lda = b.ldh;
-                const void* const R[1] = {b.H[l]}; const int rf[1] = {Fmt16<Fw<T>>::value}; const int64_t ldr[1] = {b.ldh};
-                RUN((stream_gemm<Fw<T>, EpiRevS<T>, 1>(c, n, l, true, b.A[l], b.ldh, Mc, R, rf, ldr, es, "sdf reverse layer")));
+            const bool plain = l > 0 && l != n.skip;
+            if (g_stream_enabled && (plain || b.G0b != nullptr || n.skip <= 0) && n.in[l] <= 256 && round_up(n.out[l], 64) <= 320) {
+                const void* const R[1] = {b.H[l]}; const int rf[1] = {Fmt16<Fw<T>>::value}; const int64_t ldr[1] = {l == 0 ? b.d0p : b.ldh};
+                if (plain) {
+                    EpiRevS<T> es{};
+                    es.hscale = in_scale(n, l); es.Aout = b.A[l - 1]; es.lda = b.ldh;
+                    RUN((stream_gemm<Fw<T>, EpiRevS<T>, 1>(c, n, l, true, b.A[l], b.ldh, Mc, R, rf, ldr, es, "sdf reverse layer")));
+                } else {
+                    EpiRevS<T, true> es{};
+                    es.hscale = in_scale(n, l); es.Aout = l > 0 ? b.A[l - 1] : nullptr; es.lda = b.ldh;
+                    es.dh = l == 0 ? 0 : n.in[l] - n.d0;
+                    es.qscale = l == n.skip ? kInvSqrt2 : 1.0f;
+                    es.g0 = (l == n.skip && b.G0b != nullptr) ? b.G0b : b.G0; es.ldg = round_up(n.d0, 4);
+                    RUN((stream_gemm<Fw<T>, EpiRevS<T, true>, 1>(c, n, l, true, b.A[l], b.ldh, Mc, R, rf, ldr, es, "sdf reverse layer (h0 columns)")));
+                }
                 continue;
             }
         }

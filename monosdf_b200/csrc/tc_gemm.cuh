@@ -31,6 +31,7 @@ constexpr int BM = 128;            // rows per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
+constexpr int kWgRows = 64;                           // k-rows (points) per k_tc_wgrad stage (32: 1.6x slower, per-stage handshakes dominate)
 constexpr int kWgEpiWarps = 16;                       // k_tc_wgrad: producer warp, MMA warp, 16 converter / epilogue warps (the
 constexpr int kWgThreads = (2 + kWgEpiWarps) * 32;    // conversion and the bias sums are issue-latency bound: 2 warps per scheduler were not enough)
 constexpr int kGemmThreads = (4 + kEpiWarps) * 32;    // k_tc_gemm: warpgroup 0 = {producer, MMA, 2 idle warps}, then 8 epilogue warps
@@ -481,6 +482,32 @@ struct WarpIO {
         warp_store_f32(slot, lane, row0, rows_left, C, ldc, c0, tmp, jlo, jhi, accum);
         flip = 0u;
     }
+    // The same for a 2 KB slot (k_tc_stream): two passes of 16 columns; every global store covers two rows x 64 B.
+    __device__ __forceinline__ void store_f32_narrow(float* C, int64_t ldc, int c0, const float v[32], int jlo, int jhi) const {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (jhi <= 16 * h || jlo >= 16 * h + 16) continue;      // warp-uniform
+            __syncwarp();
+            const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t)lane * 64u + (((uint32_t)p ^ sw) << 4)),
+                             "f"(v[16 * h + 4 * p]), "f"(v[16 * h + 4 * p + 1]), "f"(v[16 * h + 4 * p + 2]), "f"(v[16 * h + 4 * p + 3]) : "memory");
+            __syncwarp();
+            const int c = lane & 15, j = 16 * h + c;
+            const bool on = j >= jlo && j < jhi;
+#pragma unroll 4
+            for (int it = 0; it < 16; ++it) {
+                const int r = it * 2 + (lane >> 4);
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x)
+                             : "r"(slot + (uint32_t)r * 64u + ((((uint32_t)c >> 2) ^ (((uint32_t)r >> 1) & 3u)) << 4) + ((uint32_t)c & 3u) * 4u) : "memory");
+                if (on && r < rows_left) C[(row0 + r) * ldc + c0 + j] = x;
+            }
+        }
+        __syncwarp();
+        flip = 0u;
+    }
     static __device__ __noinline__ void warp_store_f32(uint32_t slot, int lane, int64_t row0, int rows_left, float* C, int64_t ldc,
                                                        int c0, const float* v, int jlo, int jhi, bool accum) {
         __syncwarp();
@@ -728,7 +755,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    constexpr uint32_t kBox = 64 * 128;                          // 64 k-rows x 128 B
+    constexpr uint32_t kBox = kWgRows * 128;                     // kWgRows k-rows x 128 B
     const uint32_t nbx = (uint32_t)nbx_, nby = (uint32_t)BJ / 64u;
     const uint32_t tmem_cols = nbx > 2 ? 512u : 256u;
     const uint32_t stage_bytes = (nbx + nby) * kBox;
@@ -748,7 +775,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     // Also tried: the instruction descriptor has separate format fields for A and B, but a kind::f16 MMA with one fp16
     // and one bf16 operand traps on sm_100a ("an illegal instruction was encountered"), so the conversion stays.
     const bool do_conv = x_fmt != y_fmt;
-    const int nkb = r1 > r0 ? (int)((r1 - r0 + 63) / 64) : 0;   // the last block of a split may run past r1: the host
+    const int nkb = r1 > r0 ? (int)((r1 - r0 + kWgRows - 1) / kWgRows) : 0;   // the last block of a split may run past r1: the host
                                                                  // makes rows_per_split a multiple of 64, so only the
                                                                  // global tail is ragged and TMA zero-fills it
     if (warp == 0 && lane == 0) {
@@ -778,7 +805,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
                 mbar_expect_tx(smem_u32(&bars->full[s]), stage_bytes);
                 const uint32_t st = base + s * stage_bytes;
-                const int row = (int)(r0 + (int64_t)kb * 64);
+                const int row = (int)(r0 + (int64_t)kb * kWgRows);
                 const CUtensorMap* mx = kk >= nkb ? &mapX2 : &mapX;
                 const CUtensorMap* my = kk >= nkb ? &mapY2 : &mapY;
                 for (uint32_t b = 0; b < nbx; ++b) tma_load_2d(st + b * kBox, mx, smem_u32(&bars->full[s]), i0 + (int)b * 64, row);
@@ -797,7 +824,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                 tc_fence_after();
                 const uint32_t st = base + s * stage_bytes;
 #pragma unroll
-                for (int k = 0; k < 64 / UMMA_K; ++k) {
+                for (int k = 0; k < kWgRows / UMMA_K; ++k) {
                     // MN-major SW128: 64-element groups along M/N are kBox apart (LBO), 8-row k groups 1024 B apart (SBO)
                     const uint64_t db = smem_desc(st + nbx * kBox + k * (UMMA_K * 128), kBox, 1024);
                     for (uint32_t h = 0; h < nbx / 2; ++h) {          // one 128-row accumulator per pair of X boxes
@@ -820,7 +847,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             // Thread t: column pair t % (32 nbx) of the X tile, k-rows rpg (t / (32 nbx)) .. + rpg - 1 of the 64-row block
             // (rpg = 16 for the 128-column tile, 32 for the 256-column tile); a warp reads whole 128-byte swizzle rows.
             const int t = (int)threadIdx.x - 64;
-            const int pairs = (int)nbx * 32, rpg = 64 / (kWgEpiWarps * 32 / pairs);
+            const int pairs = (int)nbx * 32, rpg = kWgRows / (kWgEpiWarps * 32 / pairs);
             const int pi = t % pairs, g = t / pairs;
             const int c = (pi & 31) * 2;
             const uint32_t box_off = (uint32_t)(pi >> 5) * kBox;
@@ -1008,12 +1035,12 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
         return MSDF_ERR_UNSUPPORTED;
     }
     CUtensorMap mX, mY, mX2, mY2;
-    int rc = make_map(&mX, X, x_fmt, M, Ci, ldx, 64, what); if (rc) return rc;
-    rc = make_map(&mY, Y, y_fmt, M, Cj, ldy, 64, what); if (rc) return rc;
+    int rc = make_map(&mX, X, x_fmt, M, Ci, ldx, kWgRows, what); if (rc) return rc;
+    rc = make_map(&mY, Y, y_fmt, M, Cj, ldy, kWgRows, what); if (rc) return rc;
     mX2 = mX; mY2 = mY;
     if (X2 != nullptr) {
-        rc = make_map(&mX2, X2, x_fmt2, M, Ci, ldx2, 64, what); if (rc) return rc;
-        rc = make_map(&mY2, Y2, y_fmt2, M, Cj, ldy2, 64, what); if (rc) return rc;
+        rc = make_map(&mX2, X2, x_fmt2, M, Ci, ldx2, kWgRows, what); if (rc) return rc;
+        rc = make_map(&mY2, Y2, y_fmt2, M, Cj, ldy2, kWgRows, what); if (rc) return rc;
     }
     const int phases = X2 != nullptr ? 2 : 1;
     const int BJ = Cj < 256 ? Cj : 256;
@@ -1024,10 +1051,10 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     rps = (rps + 63) / 64 * 64;
     if (rps < 256) rps = 256;
     splits = (int)((M + rps - 1) / rps);
-    const uint32_t stage_bytes = (nbx + BJ / 64) * 64 * 128;
+    const uint32_t stage_bytes = (nbx + BJ / 64) * kWgRows * 128;
     const size_t fixed = 1024 + sizeof(Barriers);
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
-    if (stages > 6) stages = 6;
+    if (stages > kMaxStages - 1) stages = kMaxStages - 1;
     if ((size_t)stages * stage_bytes < (size_t)kWgEpiWarps * kSlotBytes) { msdf_set_error("%s: stage ring smaller than the flush slots", what); return MSDF_ERR_ARG; }
     const size_t smem = fixed + (size_t)stages * stage_bytes;
     static bool attr_set = false;
