@@ -953,16 +953,17 @@ inline EncodeTiledFn encode_fn() {
 }
 
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows x 64 cols], 128-byte swizzle
-inline int make_map(CUtensorMap* map, const void* p, int fmt, int64_t rows, int64_t cols, int64_t ld, int box_rows, const char* who) {
+inline int make_map(CUtensorMap* map, const void* p, int fmt, int64_t rows, int64_t cols, int64_t ld, int box_rows, const char* who,
+                    int box_cols = 64) {   // 64: SWIZZLE_128B rows, 32: SWIZZLE_64B rows
     EncodeTiledFn fn = encode_fn();
     if (!fn) { msdf_set_error("%s: cuTensorMapEncodeTiled is unavailable", who); return MSDF_ERR_CUDA; }
     if ((((uintptr_t)p) & 15) != 0 || (ld % 8) != 0) { msdf_set_error("%s: TMA operand must be 16-byte aligned (ld %% 8 == 0)", who); return MSDF_ERR_ARG; }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult r = fn(map, fmt == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(p), gdim, gstr, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { msdf_set_error("%s: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%d", who, (int)r,
                                             (long long)rows, (long long)cols, (long long)ld, box_rows); return MSDF_ERR_CUDA; }

@@ -52,13 +52,14 @@ struct OpRow {
 template <class Epi>
 __global__ void __launch_bounds__(kStreamThreads, 1)
 k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW, const __grid_constant__ OpMaps ops,
-            int64_t M, int BN, int KB, int nboxes, int a_fmt, Epi epi) {
+            int64_t M, int BN, int KB, int nboxes, int a_fmt, int bk, Epi epi) {
+    // bk: columns per A / W k-block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows: half the stage, room for deeper operand rings)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     constexpr int kOps = Epi::kOps;
-    const uint32_t w_block = (uint32_t)BN * 128u;
-    const uint32_t stage_bytes = kStageBytesA + w_block;        // A k-block + W k-block
+    const uint32_t a_block = (uint32_t)BM * (uint32_t)bk * 2u, w_block = (uint32_t)BN * (uint32_t)bk * 2u;
+    const uint32_t stage_bytes = a_block + w_block;             // A k-block + W k-block
     const uint32_t sS = base;                                   // 2 stages
     const uint32_t sO = sS + 2u * stage_bytes;                  // kOps x nboxes boxes
     const uint32_t sE = sO + (uint32_t)(kOps * nboxes) * kBoxBytes;   // staging slots of the epilogue warps (output stores): 2 KB each
@@ -104,8 +105,8 @@ k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         mbar_wait(smem_u32(&bars->sempty[s]), ph ^ 1u);
                         mbar_expect_tx(smem_u32(&bars->sfull[s]), stage_bytes);
                         const uint32_t st = sS + (uint32_t)s * stage_bytes;
-                        tma_load_2d(st, &mapA, smem_u32(&bars->sfull[s]), kb * BK, (int)(tile * BM));
-                        tma_load_2d(st + kStageBytesA, &mapW, smem_u32(&bars->sfull[s]), kb * BK, 0);
+                        tma_load_2d(st, &mapA, smem_u32(&bars->sfull[s]), kb * bk, (int)(tile * BM));
+                        tma_load_2d(st + a_block, &mapW, smem_u32(&bars->sfull[s]), kb * bk, 0);
                         if (++s == 2) { s = 0; ph ^= 1u; }
                     }
             }
@@ -124,10 +125,12 @@ k_tc_stream(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         mbar_wait(smem_u32(&bars->sfull[s]), ph);
                         tc_fence_after();
                         const uint32_t st = sS + (uint32_t)s * stage_bytes;
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t da = smem_desc(st + k * (UMMA_K * 2), 16, 1024);
-                            const uint64_t db = smem_desc(st + kStageBytesA + k * (UMMA_K * 2), 16, 1024);
+                        // K-major swizzled atoms of 8 rows: 1024 B apart for 128-byte rows, 512 B for 64-byte rows
+                        const uint64_t swz = bk == 64 ? 0ull : (((uint64_t)4 << 61) ^ ((uint64_t)2 << 61));   // layout_type_ 2 -> 4 (SWIZZLE_64B)
+                        const uint32_t sbo = bk == 64 ? 1024u : 512u;
+                        for (int k = 0; k < bk / UMMA_K; ++k) {
+                            const uint64_t da = smem_desc(st + k * (UMMA_K * 2), 16, sbo) ^ swz;
+                            const uint64_t db = smem_desc(st + a_block + k * (UMMA_K * 2), 16, sbo) ^ swz;
                             umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                         umma_commit(smem_u32(&bars->sempty[s]));
@@ -229,12 +232,15 @@ int launch_stream(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, cons
     constexpr int kOps = Epi::kOps;
     CUtensorMap mA, mW;
     OpMaps ops{};
-    int rc = make_map(&mA, A, a_fmt, M, Kp, lda, BM, what); if (rc) return rc;
-    rc = make_map(&mW, W, a_fmt, BN, Kp, ldw, BN, what); if (rc) return rc;
+    // three read-back operands: 32-column k-blocks (2 x 24 KB of stages instead of 2 x 48 KB) make room for rings of 3 boxes
+    static const int bk_env = [] { const char* e = getenv("MSDF_STREAM_BK"); return e ? atoi(e) : 0; }();
+    const int bk = (bk_env == 32 || bk_env == 64) ? bk_env : (kOps >= 3 ? 32 : 64);
+    int rc = make_map(&mA, A, a_fmt, M, Kp, lda, BM, what, bk); if (rc) return rc;
+    rc = make_map(&mW, W, a_fmt, BN, Kp, ldw, BN, what, bk); if (rc) return rc;
     const int cols = (BN + 63) / 64 * 64;
     for (int o = 0; o < kOps; ++o) { rc = make_map(&ops.m[o], R[o], r_fmt[o], M, cols, ldr[o], BM, what); if (rc) return rc; }
-    const int KB = Kp / 64;
-    const size_t stage_bytes = kStageBytesA + (size_t)BN * 128;
+    const int KB = Kp / bk;
+    const size_t stage_bytes = (size_t)(BM + BN) * bk * 2;
     const size_t fixed = 1024 + sizeof(StreamBarriers) + kStreamEpiWarps * kStreamSlot + kColVecBytes + 2 * stage_bytes;
     int nboxes = kOps > 0 ? (int)((227 * 1024 - fixed) / ((size_t)kOps * kBoxBytes)) : 0;
     if (nboxes > kMaxBoxes) nboxes = kMaxBoxes;
@@ -251,7 +257,7 @@ int launch_stream(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, cons
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
                                      (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(kOps + Epi::kStores)));
-    k_tc_stream<Epi><<<grid, kStreamThreads, smem, st>>>(mA, mW, ops, M, BN, KB, nboxes, a_fmt, epi);
+    k_tc_stream<Epi><<<grid, kStreamThreads, smem, st>>>(mA, mW, ops, M, BN, KB, nboxes, a_fmt, bk, epi);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
     MSDF_CHECK_LAUNCH(what);
