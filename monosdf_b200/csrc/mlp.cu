@@ -26,6 +26,7 @@
 #include "tc_gemm.cuh"
 #include "fused_mlp.cuh"
 #include "tc_stream.cuh"
+#include "tc_chain.cuh"
 
 int msdf_hash_forward_rows(const float* x, const float* table, const int* offsets, float* out, int64_t out_ld,
                            int64_t B, int C, int L, float S, uint32_t H, float divide_factor, float* dy_dx, cudaStream_t st);
@@ -1605,9 +1606,67 @@ EpiRev<T> make_rev(const Net& n, const Bufs<T>& b, int l) {
     return e;
 }
 
+int g_chain_enabled = [] { const char* e = getenv("MSDF_CHAIN"); return e ? atoi(e) : 1; }();
+
+// The whole reverse sweep of a chunk as ONE launch (tc_chain.cuh): a_l stays on chip between the layers.
+template <class T>
+bool rev_chain_applicable(const Net& n, const Bufs<T>& b) {
+    if (!kIsBf16<T> || !g_chain_enabled || !g_stream_enabled) return false;
+    if (n.L < 2 || n.L > msdf_tc::kChainMaxSteps) return false;
+    if (n.skip > 0 && b.G0b == nullptr) return false;              // (layer 0 would have to accumulate into G0)
+    for (int l = 0; l < n.L; ++l) {
+        if (n.in[l] > 256) return false;
+        if (l < n.L - 1 && n.out[l] > 256) return false;
+    }
+    return true;
+}
+template <class T>
+int reverse_sweep_chain(const Ctx& c, const Bufs<T>& b, int64_t Mc) {
+    using namespace msdf_tc;
+    const Net& n = c.sn;
+    ChainMaps maps{};
+    ChainPlan plan{};
+    plan.ldg = round_up(n.d0, 4);
+    double flops = 0.0, bytes = 0.0;
+    int s = 0;
+    {
+        const int l = n.L - 1;
+        ChainStep& st = plan.st[s];
+        st.BN = 0; st.KB = 0; st.N = n.in[l]; st.dh = n.in[l];
+        st.nb = (round_up(n.in[l], 32) / 32 + 1) / 2; st.ob = st.nb;
+        st.hscale = in_scale(n, l); st.qscale = 1.0f; st.g0 = nullptr;
+        maps.w[s] = CUtensorMap{};
+        RUN(make_map(&maps.op[s], b.H[l], kF16, Mc, st.nb * 64, b.ldh, BM, "reverse sweep (h)"));
+        RUN(make_map(&maps.out[s], b.A[l - 1], kF16, Mc, st.ob * 64, b.ldh, BM, "reverse sweep (a)"));
+        bytes += (double)Mc * 2.0 * 64.0 * (st.nb + st.ob);
+        ++s;
+    }
+    for (int l = n.L - 2; l >= 0; --l, ++s) {
+        ChainStep& st = plan.st[s];
+        const int dh = l == 0 ? 0 : (l == n.skip ? n.in[l] - n.d0 : n.in[l]);
+        st.BN = round_up(n.in[l], 16); st.KB = round_up(n.out[l], 64) / 64; st.N = n.in[l]; st.dh = dh;
+        st.nb = l > 0 ? (round_up(st.BN, 32) / 32 + 1) / 2 : 0;
+        st.ob = l > 0 ? round_up(dh, 64) / 64 : 0;
+        st.hscale = in_scale(n, l); st.qscale = l == n.skip ? kInvSqrt2 : 1.0f;
+        st.g0 = (l == n.skip && b.G0b != nullptr) ? b.G0b : b.G0;
+        const int kp = st.KB * 64;
+        RUN(make_map(&maps.w[s], n.wt(l, kF16), kF16, st.BN, kp, kp, st.BN, "reverse sweep (W^T)", kChainBK));
+        if (st.nb > 0) RUN(make_map(&maps.op[s], b.H[l], kF16, Mc, st.nb * 64, l == 0 ? b.d0p : b.ldh, BM, "reverse sweep (h)"));
+        else maps.op[s] = maps.op[0];
+        if (st.ob > 0) RUN(make_map(&maps.out[s], b.A[l - 1], kF16, Mc, st.ob * 64, b.ldh, BM, "reverse sweep (a)"));
+        else maps.out[s] = maps.out[0];
+        flops += 2.0 * (double)Mc * st.BN * kp;
+        bytes += (double)Mc * 2.0 * 64.0 * (st.nb + st.ob) + (double)Mc * 4.0 * (st.N - dh);
+    }
+    plan.S = s;
+    RevChainPolicy pol{n.W[n.L - 1]};
+    return launch_chain(maps, plan, Mc, pol, flops, bytes, c.st, "sdf reverse sweep (chained)");
+}
+
 template <class T>
 int reverse_sweep(const Ctx& c, const Bufs<T>& b, int64_t Mc) {
     const Net& n = c.sn;
+    if (rev_chain_applicable<T>(n, b)) return reverse_sweep_chain<T>(c, b, Mc);
     {
         const int l = n.L - 1;
         const int ng = (n.in[l] + (kIsBf16<T> ? 7 : 3)) / (kIsBf16<T> ? 8 : 4);

@@ -508,6 +508,30 @@ struct WarpIO {
         __syncwarp();
         flip = 0u;
     }
+    // The same for a 1 KB slot (k_tc_chain): four passes of 8 columns; every global store covers four rows x 32 B.
+    __device__ __forceinline__ void store_f32_narrow8(float* C, int64_t ldc, int c0, const float v[32], int jlo, int jhi) const {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            if (jhi <= 8 * h || jlo >= 8 * h + 8) continue;         // warp-uniform
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot + (uint32_t)lane * 32u + (uint32_t)p * 16u),
+                             "f"(v[8 * h + 4 * p]), "f"(v[8 * h + 4 * p + 1]), "f"(v[8 * h + 4 * p + 2]), "f"(v[8 * h + 4 * p + 3]) : "memory");
+            __syncwarp();
+            const int c = lane & 7, j = 8 * h + c;
+            const bool on = j >= jlo && j < jhi;
+#pragma unroll 4
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + (lane >> 3);
+                float x;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(slot + (uint32_t)r * 32u + (uint32_t)c * 4u) : "memory");
+                if (on && r < rows_left) C[(row0 + r) * ldc + c0 + j] = x;
+            }
+        }
+        __syncwarp();
+        flip = 0u;
+    }
     static __device__ __noinline__ void warp_store_f32(uint32_t slot, int lane, int64_t row0, int rows_left, float* C, int64_t ldc,
                                                        int c0, const float* v, int jlo, int jhi, bool accum) {
         __syncwarp();
