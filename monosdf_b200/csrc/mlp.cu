@@ -363,6 +363,22 @@ k_backward_rows(const float* __restrict__ x, int64_t M, int multires, int pe_w, 
     pe_row(p, multires, pe);            // d/dx sin(f x) = f cos(f x), d/dx cos(f x) = -f sin(f x)
     T* trow = TG0 + m * ldt;
     const int d0 = pe_w + grid_w;
+    // hash columns: J_hash dn from 16-byte loads of the point's dy_dx row (two levels = three loads)
+    float hr[32];
+    const bool hvec = dy_dx != nullptr && level_dim == 2 && (n_levels & 1) == 0 && n_levels <= 16;
+    if (hvec) {
+        const float4* d4 = reinterpret_cast<const float4*>(dy_dx + m * (int64_t)(n_levels * 6));
+#pragma unroll
+        for (int l2 = 0; l2 < 8; ++l2) {
+            if (l2 < n_levels / 2) {
+                const float4 a = d4[3 * l2], b = d4[3 * l2 + 1], c = d4[3 * l2 + 2];
+                hr[4 * l2] = (a.x * v[0] + a.z * v[1] + b.x * v[2]) * hash_chain;
+                hr[4 * l2 + 1] = (a.y * v[0] + a.w * v[1] + b.y * v[2]) * hash_chain;
+                hr[4 * l2 + 2] = (b.z * v[0] + c.x * v[1] + c.z * v[2]) * hash_chain;
+                hr[4 * l2 + 3] = (b.w * v[0] + c.y * v[1] + c.w * v[2]) * hash_chain;
+            }
+        }
+    }
     for (int j0 = 0; j0 < t_cols; j0 += 8) {
         float t[8];
 #pragma unroll
@@ -375,9 +391,13 @@ k_backward_rows(const float* __restrict__ x, int64_t M, int multires, int pe_w, 
                 const float f = (float)(1 << k);
                 r = q < 3 ? f * pe[j + 3] * v[q] : -f * pe[j - 3] * v[q - 3];
             } else if (j < d0 && dy_dx != nullptr) {
-                const int qq = j - pe_w, l = qq / level_dim, c = qq - l * level_dim;
-                const float* dd = dy_dx + m * (int64_t)(n_levels * 3 * level_dim) + (l * 3) * level_dim + c;
-                r = (dd[0] * v[0] + dd[level_dim] * v[1] + dd[2 * level_dim] * v[2]) * hash_chain;
+                if (hvec) {
+                    r = hr[j - pe_w];
+                } else {
+                    const int qq = j - pe_w, l = qq / level_dim, c = qq - l * level_dim;
+                    const float* dd = dy_dx + m * (int64_t)(n_levels * 3 * level_dim) + (l * 3) * level_dim + c;
+                    r = (dd[0] * v[0] + dd[level_dim] * v[1] + dd[2 * level_dim] * v[2]) * hash_chain;
+                }
             }
             t[u] = r;
         }
@@ -425,19 +445,49 @@ __global__ void k_decode(const float* __restrict__ x, const float* __restrict__ 
     const float p[3] = {x[3 * m], x[3 * m + 1], x[3 * m + 2]};
     float g[3] = {0.f, 0.f, 0.f};
     if (g0 != nullptr) {
+        // A thread walks its own rows: 16-byte loads (ldg % 4 == 0, 16-byte aligned bases) keep the LSU transaction
+        // count down -- with scalar loads the kernel was bound by it (165 us per 262 144 points of the grid conf).
         const float* gr = g0 + m * ldg;
-        if (g0b != nullptr) {
-            const float* gb = g0b + m * ldg;
-            for (int j = 0; j < pe_w; ++j) g[pe_dim(j)] += (gr[j] + gb[j]) * pe_deriv(p, j);
-        } else {
-            for (int j = 0; j < pe_w; ++j) g[pe_dim(j)] += gr[j] * pe_deriv(p, j);
+        const float4* gr4 = reinterpret_cast<const float4*>(gr);
+        const float4* gb4 = g0b != nullptr ? reinterpret_cast<const float4*>(g0b + m * ldg) : nullptr;
+        float pe[kMaxPe];
+        pe_row(p, (pe_w - 3) / 6, pe);      // d/dx sin(f x) = f cos(f x), d/dx cos(f x) = -f sin(f x): the row's own entries
+        for (int c4 = 0; 4 * c4 < pe_w; ++c4) {
+            float4 a = gr4[c4];
+            if (gb4 != nullptr) { const float4 b = gb4[c4]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = 4 * c4 + e;
+                if (j >= pe_w) break;
+                float dv = 1.0f; int dim = j;
+                if (j >= 3) {
+                    const int k = (j - 3) / 6, q = (j - 3) - 6 * k;
+                    const float f = (float)(1 << k);
+                    dv = q < 3 ? f * pe[j + 3] : -f * pe[j - 3];
+                    dim = q < 3 ? q : q - 3;
+                }
+                const float t = av[e] * dv;
+                if (dim == 0) g[0] += t; else if (dim == 1) g[1] += t; else g[2] += t;
+            }
         }
         if (grid_w > 0 && dy_dx != nullptr) {
             const float* dd = dy_dx + m * (int64_t)(n_levels * 3 * level_dim);
             float h[3] = {0.f, 0.f, 0.f};
-            for (int l = 0; l < n_levels; ++l)
-                for (int d = 0; d < 3; ++d)
-                    for (int c = 0; c < level_dim; ++c) h[d] += gr[pe_w + l * level_dim + c] * dd[(l * 3 + d) * level_dim + c];
+            if (level_dim == 2 && (n_levels & 1) == 0) {     // two levels = 12 derivatives = three 16-byte loads
+                const float4* d4 = reinterpret_cast<const float4*>(dd);
+                for (int l2 = 0; l2 < n_levels / 2; ++l2) {
+                    const float4 a = d4[3 * l2], b = d4[3 * l2 + 1], c = d4[3 * l2 + 2];
+                    const float* gg = gr + pe_w + 4 * l2;
+                    const float g0v = gg[0], g1v = gg[1], g2v = gg[2], g3v = gg[3];
+                    h[0] += g0v * a.x; h[0] += g1v * a.y; h[1] += g0v * a.z; h[1] += g1v * a.w; h[2] += g0v * b.x; h[2] += g1v * b.y;
+                    h[0] += g2v * b.z; h[0] += g3v * b.w; h[1] += g2v * c.x; h[1] += g3v * c.y; h[2] += g2v * c.z; h[2] += g3v * c.w;
+                }
+            } else {
+                for (int l = 0; l < n_levels; ++l)
+                    for (int d = 0; d < 3; ++d)
+                        for (int c = 0; c < level_dim; ++c) h[d] += gr[pe_w + l * level_dim + c] * dd[(l * 3 + d) * level_dim + c];
+            }
             g[0] += h[0] * hash_chain; g[1] += h[1] * hash_chain; g[2] += h[2] * hash_chain;
         }
     }
