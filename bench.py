@@ -190,20 +190,11 @@ def run_reference(args):
     os.environ["CUDA_VISIBLE_DEVICES"] = ""          # host cores only: the reference's hard-coded .cuda() calls become no-ops
     cores = args.cpu_threads or os.cpu_count() or 1
     n = args.cpu_rays
-    # the reference's constructors and loss print to stdout (network.py / loss.py); the contract is ONE JSON line there
-    sys.stdout.flush()
-    real_stdout = os.dup(1)
-    os.dup2(2, 1)
-    try:
-        t, kind = cpu_reference_step_time(args.beta, n, args.steps, args.warmup, cores)
-        t1 = None
-        if not args.cpu_threads and cores > 1:
-            # the reference trainer itself runs with torch.set_num_threads(1) (monosdf_train.py:37): one bounded step of that too
-            t1, _ = cpu_reference_step_time(args.beta, n, 1, 1, 1)
-    finally:
-        sys.stdout.flush()
-        os.dup2(real_stdout, 1)
-        os.close(real_stdout)
+    t, kind = cpu_reference_step_time(args.beta, n, args.steps, args.warmup, cores)
+    t1 = None
+    if not args.cpu_threads and cores > 1:
+        # the reference trainer itself runs with torch.set_num_threads(1) (monosdf_train.py:37): one bounded step of that too
+        t1, _ = cpu_reference_step_time(args.beta, n, 1, 1, 1)
     v = n / t
     what = "the reference's own model/network.py + model/loss.py + torch.optim.Adam" if kind == "reference" else \
         "oracle/port.py (restatement of the reference, pinned by tests/test_oracle_golden.py) + torch.optim.Adam"
@@ -221,7 +212,7 @@ def run_reference(args):
     if t1 is not None:
         line["cpu_baseline_1thread"] = {"value": n / t1, "unit": UNIT, "cores": 1, "kind": kind,
                                         "sample": "one timed %d-ray step after one warm-up, 1 thread (monosdf_train.py:37)" % n}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -620,13 +611,25 @@ def run_ours(args):
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as e:      # noqa: BLE001
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The contract's ONE JSON line, on the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     a = parse()
+    # stdout carries the JSON line only: whatever libraries print there (NCCL's version banner under torchrun, the
+    # reference's constructors and loss) goes to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if a.impl == "reference":
         run_reference(a)
     else:
