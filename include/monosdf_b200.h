@@ -281,6 +281,12 @@ int msdf_tc_selftest_count(void);
  * sweep (A/B measurements, tests); default 1. */
 void msdf_set_fused(int on);
 
+/* Backward-side sweeps of the tensor-core mode (the analytic replacement of autograd's double backward through
+ * network.py:79-109): stream != 0 runs the per-layer kernels with every operand fed by TMA (csrc/tc_stream.cuh) instead
+ * of the round-1 engine (csrc/tc_gemm.cuh); chain != 0 additionally runs the reverse sweep of a chunk as ONE launch with
+ * its state on chip (csrc/tc_chain.cuh).  Same arithmetic on every path (A/B measurements, tests); default 1, 1. */
+void msdf_set_sweeps(int stream, int chain);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "msdf_tc_selftest": (c_int, [c_int, POINTER(c_float), _P]),
     "msdf_tc_selftest_count": (c_int, []),
     "msdf_set_fused": (None, [c_int]),
+    "msdf_set_sweeps": (None, [c_int, c_int]),
     "msdf_profile_enable": (c_int, [c_int]),
     "msdf_profile_read": (c_int, [c_int, POINTER(ctypes.c_double), POINTER(ctypes.c_double), POINTER(ctypes.c_longlong), c_int]),
     "msdf_profile_read_bytes": (c_int, [c_int, POINTER(ctypes.c_double)]),

@@ -2430,6 +2430,7 @@ extern "C" int msdf_field_backward(const msdf_mlp_desc* sdf_net, const msdf_enco
 }
 
 extern "C" void msdf_set_fused(int on) { g_fused_enabled = on; }
+extern "C" void msdf_set_sweeps(int stream, int chain) { g_stream_enabled = stream; g_chain_enabled = chain; }
 
 extern "C" int msdf_ray_points(const float* ray_o, const float* ray_d, const float* z, int64_t n_rays, int n, float* points,
                                void* stream) {
