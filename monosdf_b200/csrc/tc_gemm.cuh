@@ -31,7 +31,7 @@ constexpr int BM = 128;            // rows per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 per 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kEpiWarps = 8;
-constexpr int kWgRows = 64;                           // k-rows (points) per k_tc_wgrad stage (32: 1.6x slower, per-stage handshakes dominate)
+constexpr int kWgRows = 64;                           // k-rows (points) per k_tc_wgrad stage (measured per 256x256 pair: 32 rows 187 us, 48 rows 150, 64 rows 114, 96 rows 118)
 constexpr int kWgEpiWarps = 16;                       // k_tc_wgrad: producer warp, MMA warp, 16 converter / epilogue warps (the
 constexpr int kWgThreads = (2 + kWgEpiWarps) * 32;    // conversion and the bias sums are issue-latency bound: 2 warps per scheduler were not enough)
 constexpr int kGemmThreads = (4 + kEpiWarps) * 32;    // k_tc_gemm: warpgroup 0 = {producer, MMA, 2 idle warps}, then 8 epilogue warps
@@ -889,7 +889,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
                     // all of a thread's vectors are loaded before the first is converted: one shared-memory latency per
                     // stage instead of one per vector (ncu source page, one vector per trip: 32 % of the kernel's samples
                     // on the first conversion after the LDS.128, short scoreboard)
-                    constexpr int kConvU = 4;                       // 4 boxes x 512 vectors / 512 threads
+                    constexpr int kConvU = (kWgRows * 32 + kWgEpiWarps * 32 - 1) / (kWgEpiWarps * 32);   // 4 boxes x 8 kWgRows vectors / 512 threads
                     uint32_t w[kConvU][4];
 #pragma unroll
                     for (int u = 0; u < kConvU; ++u) {
@@ -1073,8 +1073,8 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     const int it = (Ci + nbx * 64 - 1) / (nbx * 64), jt = (Cj + BJ - 1) / BJ;
     int splits = (sm_count() + it * jt - 1) / (it * jt);
     int64_t rps = (M + splits - 1) / splits;
-    rps = (rps + 63) / 64 * 64;
-    if (rps < 256) rps = 256;
+    rps = (rps + kWgRows - 1) / kWgRows * kWgRows;
+    if (rps < 4 * kWgRows) rps = 4 * kWgRows;
     splits = (int)((M + rps - 1) / rps);
     const uint32_t stage_bytes = (nbx + BJ / 64) * kWgRows * 128;
     const size_t fixed = 1024 + sizeof(Barriers);
