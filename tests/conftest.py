@@ -31,5 +31,5 @@ def golden():
     import torch
 
     def load(name):
-        return torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=False)
+        return torch.load(os.path.join(GOLDEN, name + ".pt"), map_location="cpu", weights_only=True)
     return load
