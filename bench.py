@@ -330,6 +330,8 @@ def profile_classes(wl, timed, steps):
     t = timed(wl.step_resident, steps)
     _lib.profile_enable(False)
     prof = {c: tuple(v / steps for v in _lib.profile_read(c, reset=False)) for c in range(5)}
+    for k in range(1, 7):          # sub-classes of the tcgen05 class (include/monosdf_b200.h)
+        prof[1 | (k << 8)] = tuple(v / steps for v in _lib.profile_read(1 | (k << 8), reset=False))
     _lib.profile_read(0, reset=True)
     return prof, t / steps
 
@@ -567,6 +569,22 @@ def run_ours(args):
             if bound == "issue":
                 others[name]["note"] = ("issue/SFU-bound by design (ncu: issue slots 72 % busy, XU 24 %, DRAM < 1 %): the byte "
                                         "figure is reported for completeness, not as its roofline")
+    # every tcgen05 kernel against the roofline that bounds IT: the fused sdf-only network against the tensor peak, everything
+    # that streams saved activations (training forward, sweeps, weight gradients) against the measured copy bandwidth
+    kernels = {}
+    for k, name, bound in ((1, "k_fused_sdf (sdf-only passes of the sampler)", "tensor"),
+                           (2, "k_fused_sdf (forward sweep of the step, activations saved)", "hbm"),
+                           (3, "k_tc_chain (reverse sweep)", "hbm"), (4, "k_tc_stream (tangent / backward layers)", "hbm"),
+                           (5, "k_tc_gemm (colour network layers)", "hbm"), (6, "k_tc_wgrad (weight gradients)", "hbm")):
+        k_ms, k_flops, k_n, k_bytes = prof.get(1 | (k << 8), (0.0, 0.0, 0, 0.0))
+        if not k_n or k_ms <= 0:
+            continue
+        if bound == "tensor":
+            ach, pk, unit = k_flops / 1e12 / (k_ms / 1e3), peak_tf, "TFLOP/s"
+        else:
+            ach, pk, unit = k_bytes / 1e9 / (k_ms / 1e3), peak_bw, "GB/s"
+        kernels[name] = {"bound": bound, "achieved": ach, "peak": pk, "unit": unit, "frac": ach / pk if pk else None,
+                         "launches": k_n, "ms_per_step": k_ms, "share_of_step": k_ms / t_prof if t_prof > 0 else None}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.total_rays else "weak", "vs_baseline": None,
@@ -597,6 +615,9 @@ def run_ours(args):
                      "step_frac": (alg_flops_step / 1e12) / (ms / args.steps / 1e3) / peak_tf,
                      # the bound that applies to a per-layer GEMM moving 1-2.5 KB per 131 KFLOP: algorithmic bytes / time
                      "hbm_view": {"achieved": gbs, "peak": peak_bw, "unit": "GB/s", "frac": gbs / peak_bw if peak_bw else None},
+                     "tcgen05_kernels": kernels,
+                     "tcgen05_kernels_note": "executed 2MNK (fused sdf-only) or algorithmic bytes (the rest) of each kernel's launches / "
+                                             "their CUDA-event time in the instrumented steps, against the roofline that bounds that kernel",
                      "other_kernels": others},
     }
     if sub:

@@ -34,8 +34,10 @@ int msdf_abi_version(void);
 unsigned long long msdf_launch_count(void);
 
 /* Per-launch device timing of the dominant kernels (CUDA events on the launching stream), for bench.py's roofline
- * line.  class: 0 fp32 GEMM, 1 tensor-core GEMM, 2 hash grid, 3 sampler, 4 compositing.  work = FLOPs (GEMMs) or
- * algorithmic bytes (the others) summed over the recorded launches. */
+ * line.  class: 0 fp32 GEMM, 1 tensor-core kernels, 2 hash grid, 3 sampler, 4 compositing.  work = FLOPs (GEMMs) or
+ * algorithmic bytes (the others) summed over the recorded launches.  Class 1 has sub-classes, read with
+ * cls = 1 | k << 8: k = 1 fused SDF network (sdf-only), 2 fused SDF network (forward sweep of a step), 3 chained reverse
+ * sweep, 4 per-layer sweeps with TMA-fed operands, 5 per-layer engine of round 1 (colour net), 6 weight gradients. */
 int msdf_profile_enable(int on);
 int msdf_profile_read(int cls, double* total_ms, double* total_work, long long* count, int reset);
 int msdf_profile_read_bytes(int cls, double* total_bytes);   /* algorithmic bytes of the same launches */

@@ -43,7 +43,7 @@ extern "C" int msdf_profile_enable(int on) {
 // Sum of the algorithmic bytes of the recorded launches of class `cls` (call before a resetting msdf_profile_read).
 extern "C" int msdf_profile_read_bytes(int cls, double* total_bytes) {
     double b = 0.0;
-    for (auto& r : g_prof) if (r.cls == cls) b += r.bytes;
+    for (auto& r : g_prof) if (cls < 256 ? (r.cls & 255) == cls : r.cls == cls) b += r.bytes;
     if (total_bytes) *total_bytes = b;
     return MSDF_OK;
 }
@@ -53,7 +53,7 @@ extern "C" int msdf_profile_read(int cls, double* total_ms, double* total_work, 
     MSDF_CUDA_CALL(cudaDeviceSynchronize());
     double ms = 0.0, work = 0.0; long long n = 0;
     for (auto& r : g_prof) {
-        if (r.cls != cls) continue;
+        if (cls < 256 ? (r.cls & 255) != cls : r.cls != cls) continue;
         float t = 0.f;
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms += t; work += r.work; ++n; }
     }

@@ -51,5 +51,9 @@ extern unsigned long long g_msdf_launches;
 // Optional per-launch device timing (CUDA events on the launching stream) of the dominant kernels, read by
 // bench.py for the roofline line.  Disabled by default: msdf_prof_begin returns -1 and records nothing.
 enum { MSDF_PROF_GEMM_F32 = 0, MSDF_PROF_GEMM_TC = 1, MSDF_PROF_HASH = 2, MSDF_PROF_SAMPLER = 3, MSDF_PROF_RENDER = 4, MSDF_PROF_CLASSES = 5 };
+// sub-classes of the tcgen05 class (class id | sub << 8): msdf_profile_read(1, ..) sums all of them, msdf_profile_read(1 | k << 8, ..) one
+enum { MSDF_PROF_TC_FUSED_SDF = MSDF_PROF_GEMM_TC | (1 << 8), MSDF_PROF_TC_FUSED_TRAIN = MSDF_PROF_GEMM_TC | (2 << 8),
+       MSDF_PROF_TC_CHAIN = MSDF_PROF_GEMM_TC | (3 << 8), MSDF_PROF_TC_STREAM = MSDF_PROF_GEMM_TC | (4 << 8),
+       MSDF_PROF_TC_GEMM = MSDF_PROF_GEMM_TC | (5 << 8), MSDF_PROF_TC_WGRAD = MSDF_PROF_GEMM_TC | (6 << 8) };
 int msdf_prof_begin(int cls, double work, cudaStream_t st, double bytes = 0.0);   // work: FLOPs; bytes: algorithmic bytes
 void msdf_prof_end(int slot, cudaStream_t st);

@@ -2109,7 +2109,7 @@ int fused_launch(const Ctx& c, const FusedPrep& fp, bool train, const float* x, 
     const int gw = c.grid ? c.enc->grid_feat_dim : 0;
     const double bytes = train ? (double)Mc * (16.0 + 4.0 * gw + 2.0 * (round_up(n.d0, 64) + 256.0 * L + (feat ? 256.0 : 0.0)))
                                : (double)Mc * (16.0 + 4.0 * gw);
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)Mc * 256.0 * kcols, c.st, bytes);
+    const int prof = msdf_prof_begin(train ? MSDF_PROF_TC_FUSED_TRAIN : MSDF_PROF_TC_FUSED_SDF, 2.0 * (double)Mc * 256.0 * kcols, c.st, bytes);
     kerns[variant]<<<grid, mf::kFusedThreads, smem, c.st>>>(fp.mW, P, sm ? *sm : no_maps, x, hashf, Mc, sdf);
     msdf_prof_end(prof, c.st);
     LAUNCHED("fused sdf network");

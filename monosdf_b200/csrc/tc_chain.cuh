@@ -329,7 +329,7 @@ int launch_chain(const ChainMaps& maps, const ChainPlan& plan, int64_t M, const 
     }
     const int64_t pairs = (M + 2 * BM - 1) / (2 * BM);
     const int grid = (int)(pairs < sm_count() ? pairs : sm_count());
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, flops, st, bytes);
+    const int prof = msdf_prof_begin(MSDF_PROF_TC_CHAIN, flops, st, bytes);
     k_tc_chain<Pol><<<grid, kStreamThreads, kChainSmem, st>>>(maps, plan, M, pol);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();

@@ -1034,7 +1034,7 @@ int launch_gemm(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, const 
     const int64_t tiles = (M + BM - 1) / BM;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
     // algorithmic bytes: the A tile once, plus every bf16 operand the epilogue reads back and writes (epi.N real columns)
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
+    const int prof = msdf_prof_begin(MSDF_PROF_TC_GEMM, 2.0 * (double)M * (double)BN * (double)Kp, st,
                                      (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(Epi::kPre + Epi::kStores)));
     k_tc_gemm<Epi><<<grid, kGemmThreads, smem, st>>>(mA, mW, M, BN, KB, stages, abytes, a_fmt, w_fmt, epi);
     msdf_prof_end(prof, st);
@@ -1089,7 +1089,7 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
         attr_set = true;
     }
     dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * phases * (double)M * (double)Ci * (double)Cj, st, phases * (double)M * 2.0 * (double)(Ci + Cj));
+    const int prof = msdf_prof_begin(MSDF_PROF_TC_WGRAD, 2.0 * phases * (double)M * (double)Ci * (double)Cj, st, phases * (double)M * 2.0 * (double)(Ci + Cj));
     k_tc_wgrad<Epi><<<grid, kWgThreads, smem, st>>>(mX, mY, M, nbx, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift,
                                                   mX2, mY2, x_fmt2, y_fmt2, phases);
     msdf_prof_end(prof, st);

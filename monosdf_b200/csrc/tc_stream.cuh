@@ -255,7 +255,7 @@ int launch_stream(const void* A, int a_fmt, int64_t lda, int64_t M, int Kp, cons
     }
     const int64_t tiles = (M + BM - 1) / BM;
     const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-    const int prof = msdf_prof_begin(MSDF_PROF_GEMM_TC, 2.0 * (double)M * (double)BN * (double)Kp, st,
+    const int prof = msdf_prof_begin(MSDF_PROF_TC_STREAM, 2.0 * (double)M * (double)BN * (double)Kp, st,
                                      (double)M * 2.0 * ((double)Kp + (double)epi.N * (double)(kOps + Epi::kStores)));
     k_tc_stream<Epi><<<grid, kStreamThreads, smem, st>>>(mA, mW, ops, M, BN, KB, nboxes, a_fmt, bk, epi);
     msdf_prof_end(prof, st);
