@@ -190,3 +190,29 @@ def test_backward_sweep_engines_agree(conf_name):
             worst = max(worst, d)
             assert d < 5e-3, (k, d)
     print("REPORT backward sweep engines (%s conf): worst parameter-gradient distance between engines %.2e" % (conf_name, worst))
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 255, 257, 148 * 256 + 1])
+def test_chained_reverse_sweep_ragged_sizes(n):
+    """grad_x sdf (ImplicitNetwork.gradient_sdf, network.py:98-109) through the chained reverse sweep at point counts around
+    the 128-row sub-tile / 256-row pair boundaries: against the fp32 path and against the per-layer engines."""
+    from monosdf_b200 import _lib
+    model = _model(confs.SCANNET_MLP)
+    inet = model.implicit_network
+    x = _points(n, seed=100 + n, spread=0.5)
+    model.set_precision("fp32")
+    with torch.no_grad():
+        ref = inet.gradient_sdf(x).clone()
+    model.set_precision("bf16")
+    out = {}
+    for name, (stream, chain) in {"chain": (1, 1), "stream": (1, 0), "gemm": (0, 0)}.items():
+        _lib.lib().msdf_set_sweeps(stream, chain)
+        try:
+            with torch.no_grad():
+                out[name] = inet.gradient_sdf(x).clone()
+        finally:
+            _lib.lib().msdf_set_sweeps(1, 1)
+    assert torch.isfinite(out["chain"]).all()
+    assert rel_err(out["chain"], ref) < BF16_TOL, rel_err(out["chain"], ref)
+    assert rel_err(out["chain"], out["stream"]) < 1e-3
+    assert rel_err(out["chain"], out["gemm"]) < 1e-3
