@@ -594,7 +594,7 @@ def run_ours(args):
                    "stationary": "parameters and Adam state restored from a snapshot before every step (%d-byte copies)" % (3 * wl.grad_bytes),
                    "precision_mode": args.precision, "parallelism": "ray-sharded dp%d, one NCCL all-reduce of the flat gradient arena" % world,
                    "l2_policy": "inputs larger than L2: every field chunk streams %.1f GB of activations through HBM (L2 is 126 MB)"
-                                % (min(n * 98, 262144) * 9.9e3 / 1e9)},
+                                % (min(n * 98, 1060864) * 9.9e3 / 1e9)},
         "clocks": clk,
         "e2e": {"value": rays_per_step * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": wl.h2d_bytes, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),

@@ -1434,10 +1434,14 @@ size_t carve(const Ctx& cx, int64_t Mc, int mode, void* ws, Bufs<T>* out, Net* s
     return c.off;
 }
 
-// Points per chunk in bf16 mode (experiment knob MSDF_CHUNK_POINTS; default 262144)
+// Points per chunk in bf16 mode (knob MSDF_CHUNK_POINTS).  Default 1 060 864 = 148 SMs x 256 rows x 28: whole waves of the
+// persistent kernels' 256-row tiles, and a quarter of the launches of the 262 144-point chunks of round 1 (measured on
+// one box, 65 536-ray step: 262 144 -> 454 k rays/s, 795 648 -> 473 k, 1 060 864 -> 475 k, 2 121 728 -> 477 k; the
+// per-call workspace grows with the chunk: 7.7 GB here).
+constexpr int64_t kChunkPointsBf16 = 1060864;
 inline int64_t chunk_cap_bf16() {
     static int64_t v = 0;
-    if (!v) { const char* e = getenv("MSDF_CHUNK_POINTS"); v = e ? atoll(e) : 262144; if (v < 1024) v = 262144; }
+    if (!v) { const char* e = getenv("MSDF_CHUNK_POINTS"); v = e ? atoll(e) : kChunkPointsBf16; if (v < 1024) v = kChunkPointsBf16; }
     return v;
 }
 

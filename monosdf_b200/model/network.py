@@ -25,7 +25,8 @@ from .embedder import get_embedder
 from .ray_sampler import ErrorBoundSampler
 
 _GB = 1 << 30
-WORKSPACE_CAP_BYTES = 6 * _GB     # per-call scratch; the library chunks the points to fit
+WORKSPACE_CAP_BYTES = int(os.environ.get("MSDF_WORKSPACE_CAP_GB", "24")) * _GB     # per-call scratch (7.7 GB for a full chunk of the MLP conf)
+CHUNK_POINTS_BF16 = 1060864        # points per chunk of the tensor-core mode: csrc/mlp.cu kChunkPointsBf16 (148 SMs x 256 rows x 28)
 # Training keeps every layer's activations of a field evaluation in HBM between forward and backward (~10 KB per point
 # in bf16 mode, 64 GB for a 65536-ray step) instead of recomputing them, when they fit in this fraction of the FREE
 # device memory; set to 0 to always recompute.
@@ -159,7 +160,7 @@ class _FieldSpec:
 
 
 def _workspace_for(sdf_d, enc_d, col_d, cd_d, M, mode, flags, device):
-    base = int(os.environ.get("MSDF_CHUNK_POINTS", "262144"))
+    base = int(os.environ.get("MSDF_CHUNK_POINTS", str(CHUNK_POINTS_BF16)))
     cap = 2 * base if mode == _lib.MODE_SDF_ONLY else (base if flags & _lib.FLAG_TENSOR_BF16 else 65536)
     chunk = min(max(int(M), 128), cap)
     need = _lib.lib().msdf_field_workspace_bytes(sdf_d, enc_d, col_d, cd_d, chunk, mode, flags)
