@@ -16,9 +16,12 @@
 //
 // The sweeps are written once, generic over the activation element type T:
 //   T = float          fp32 mode: SIMT FFMA GEMMs (gemm_f32.cuh), the reference's arithmetic class (1e-4 parity)
-//   T = __nv_bfloat16  tensor-core mode: tcgen05 GEMMs with TMEM accumulators and TMA-fed operands (tc_gemm.cuh),
-//                      forward-like matrices stored in fp16, adjoint-like ones in bf16 (Fw<T> below), fp32
-//                      accumulation (2e-2 parity)
+//   T = __nv_bfloat16  tensor-core mode: tcgen05 kernels with TMEM accumulators and TMA-fed operands -- the forward sweep
+//                      and the sdf-only queries as ONE kernel with the activations on chip (fused_mlp.cuh), the reverse
+//                      sweep as one chained kernel (tc_chain.cuh), tangent / backward layers with every operand streamed
+//                      by TMA (tc_stream.cuh; z_l is rebuilt in the backward epilogue instead of stored), weight
+//                      gradients and the colour net on tc_gemm.cuh; forward-like matrices stored in fp16, adjoint-like
+//                      ones in bf16 (Fw<T> below), fp32 accumulation (2e-2 parity)
 #include <stdlib.h>
 #include <type_traits>
 
