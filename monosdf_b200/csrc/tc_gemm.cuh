@@ -768,10 +768,15 @@ k_tc_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 // The kernel is bound by shared-memory bandwidth (per stage: TMA writes + MMA operand reads + the format conversion
 // below), so the 256-column X tile matters: the Y boxes are written / converted once for two accumulators' worth of
 // MMAs (per 128x256 unit of work 112 KB instead of 160 KB of shared-memory traffic in the mixed-format products).
+// Output tiles of one weight-gradient launch and the CTAs (row splits) each of them gets: a remainder tile along Y (the 64
+// columns a 320-wide operand has beyond 256: the 289-wide colour input layer) loads and multiplies only its own boxes and
+// receives CTAs in proportion to its shared-memory traffic instead of half of the grid.
+struct WgTiles { int n; int first[5]; int i0[4], j0[4], nbx[4], bj[4]; long long rps[4]; };
+
 template <class Epi>
 __global__ void __launch_bounds__(kWgThreads, 1)
-k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int nbx_, int BJ,
-           int64_t rows_per_split, int stages, int x_fmt, int y_fmt, Epi epi, float* __restrict__ colsum, int colsum_n,
+k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY, int64_t Mrows, int nbx_, int BJ_,
+           const __grid_constant__ WgTiles tiles, int stages, int x_fmt, int y_fmt, Epi epi, float* __restrict__ colsum, int colsum_n,
            int colsum_perm, int colsum_shift, const __grid_constant__ CUtensorMap mapX2, const __grid_constant__ CUtensorMap mapY2,
            int x_fmt2, int y_fmt2, int phases) {
     // phases == 2: dW += X^T Y + X2^T Y2 in ONE launch (the two weight-gradient products of a layer, pbar^T h and a^T t:
@@ -780,16 +785,21 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
     constexpr uint32_t kBox = kWgRows * 128;                     // kWgRows k-rows x 128 B
-    const uint32_t nbx = (uint32_t)nbx_, nby = (uint32_t)BJ / 64u;
+    int tile = 0;
+    while (tile + 1 < tiles.n && (int)blockIdx.x >= tiles.first[tile + 1]) ++tile;
+    const int BJ = tiles.bj[tile];
+    const uint32_t nbx = (uint32_t)tiles.nbx[tile], nby = (uint32_t)BJ / 64u;
     const uint32_t tmem_cols = nbx > 2 ? 512u : 256u;
-    const uint32_t stage_bytes = (nbx + nby) * kBox;
+    const uint32_t stage_bytes = ((uint32_t)nbx_ + (uint32_t)BJ_ / 64u) * kBox;   // stride of the ring: the launch's largest tile
+    const uint32_t stage_tx = (nbx + nby) * kBox;                                  // bytes this CTA's tile loads per stage
     const uint32_t sE = base;   // the flush's staging slots reuse the stage ring (idle by then; host: ring >= 16 slots)
     Barriers* bars = reinterpret_cast<Barriers*>(gen_base + (size_t)stages * stage_bytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i0 = blockIdx.x * (int)(nbx * 64u), j0 = blockIdx.y * BJ;
-    const int64_t r0 = (int64_t)blockIdx.z * rows_per_split;
+    const int i0 = tiles.i0[tile], j0 = tiles.j0[tile];
+    const int64_t rows_per_split = tiles.rps[tile];
+    const int64_t r0 = (int64_t)((int)blockIdx.x - tiles.first[tile]) * rows_per_split;
     const int64_t r1 = (r0 + rows_per_split < Mrows) ? r0 + rows_per_split : Mrows;
-    const bool do_colsum = colsum != nullptr && blockIdx.y == 0;   // out[i] += sum_m X[m, i]: bias gradients for free
+    const bool do_colsum = colsum != nullptr && j0 == 0;   // out[i] += sum_m X[m, i]: bias gradients for free
     // mixed formats (pbar^T h, a^T t: one adjoint-like bf16 operand, one forward-like fp16 operand): the epilogue
     // warps, idle during the main loop, round the fp16 boxes of every stage to bf16 in place before the MMAs read them.
     // The kernel is bound by shared-memory bandwidth (TMA write + MMA read = 96 KB per stage; the conversion adds a
@@ -827,7 +837,7 @@ k_tc_wgrad(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUt
             for (int kk = 0; kk < nkb * phases; ++kk) {
                 const int kb = kk >= nkb ? kk - nkb : kk;
                 mbar_wait(smem_u32(&bars->empty[s]), ph ^ 1u);
-                mbar_expect_tx(smem_u32(&bars->full[s]), stage_bytes);
+                mbar_expect_tx(smem_u32(&bars->full[s]), stage_tx);
                 const uint32_t st = base + s * stage_bytes;
                 const int row = (int)(r0 + (int64_t)kb * kWgRows);
                 const CUtensorMap* mx = kk >= nkb ? &mapX2 : &mapX;
@@ -1071,11 +1081,37 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
     const int BJ = Cj < 256 ? Cj : 256;
     const int nbx = Ci > 128 ? 4 : 2;                       // X tile of 256 (two accumulators) or 128 columns
     const int it = (Ci + nbx * 64 - 1) / (nbx * 64), jt = (Cj + BJ - 1) / BJ;
-    int splits = (sm_count() + it * jt - 1) / (it * jt);
-    int64_t rps = (M + splits - 1) / splits;
-    rps = (rps + kWgRows - 1) / kWgRows * kWgRows;
-    if (rps < 4 * kWgRows) rps = 4 * kWgRows;
-    splits = (int)((M + rps - 1) / rps);
+    if (it * jt > 4) { msdf_set_error("%s: more than 4 output tiles", what); return MSDF_ERR_ARG; }
+    WgTiles tiles{};
+    double cost[4], total_cost = 0.0;
+    for (int ti = 0; ti < it; ++ti)
+        for (int tj = 0; tj < jt; ++tj) {
+            const int t = tiles.n++;
+            const int xb = (Ci - ti * nbx * 64) / 64, yc = Cj - tj * BJ;
+            tiles.i0[t] = ti * nbx * 64; tiles.j0[t] = tj * BJ;
+            tiles.nbx[t] = nbx;      // (a remainder X tile trimmed to 128 columns costs as much per stage as a full one: measured)
+            (void)xb;
+            tiles.bj[t] = yc < BJ ? yc : BJ;
+            const int bx = tiles.nbx[t], by = tiles.bj[t] / 64;
+            // shared-memory traffic of a stage in KB-ish units: TMA writes, MMA reads (B once per accumulator), the
+            // conversion's read + write of the fp16 operand, the bias sums
+            cost[t] = 8.0 * (bx + by) + (bx / 2) * (16.0 + 8.0 * by) + (x_fmt != y_fmt ? 16.0 * (x_fmt == kF16 ? bx : by) : 0.0) +
+                      (colsum != nullptr && tj == 0 ? 8.0 * bx : 0.0);
+            // measured (1 060 864 rows): a [256 x 64] tile's stage takes 0.45-0.5 of a [256 x 256] tile's, as modelled
+            total_cost += cost[t];
+        }
+    int grid_ctas = 0;
+    for (int t = 0; t < tiles.n; ++t) {
+        int splits = (int)(sm_count() * cost[t] / total_cost + 0.5);
+        if (splits < 1) splits = 1;
+        int64_t rps = (M + splits - 1) / splits;
+        rps = (rps + kWgRows - 1) / kWgRows * kWgRows;
+        if (rps < 4 * kWgRows) rps = 4 * kWgRows;
+        splits = (int)((M + rps - 1) / rps);
+        tiles.rps[t] = rps; tiles.first[t] = grid_ctas;
+        grid_ctas += splits;
+    }
+    tiles.first[tiles.n] = grid_ctas;
     const uint32_t stage_bytes = (nbx + BJ / 64) * kWgRows * 128;
     const size_t fixed = 1024 + sizeof(Barriers);
     int stages = (int)((227 * 1024 - fixed) / stage_bytes);
@@ -1088,9 +1124,9 @@ int launch_wgrad(const void* X, int x_fmt, int64_t ldx, int Ci, const void* Y, i
         if (e != cudaSuccess) { msdf_set_error("%s: cannot opt in to 227 KB shared memory: %s", what, cudaGetErrorString(e)); return MSDF_ERR_CUDA; }
         attr_set = true;
     }
-    dim3 grid((unsigned)it, (unsigned)jt, (unsigned)splits);
+    dim3 grid((unsigned)grid_ctas, 1, 1);
     const int prof = msdf_prof_begin(MSDF_PROF_TC_WGRAD, 2.0 * phases * (double)M * (double)Ci * (double)Cj, st, phases * (double)M * 2.0 * (double)(Ci + Cj));
-    k_tc_wgrad<Epi><<<grid, kWgThreads, smem, st>>>(mX, mY, M, nbx, BJ, rps, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift,
+    k_tc_wgrad<Epi><<<grid, kWgThreads, smem, st>>>(mX, mY, M, nbx, BJ, tiles, stages, x_fmt, y_fmt, epi, colsum, colsum_n, colsum_perm, colsum_shift,
                                                   mX2, mY2, x_fmt2, y_fmt2, phases);
     msdf_prof_end(prof, st);
     MSDF_COUNT_LAUNCH();
